@@ -1,0 +1,198 @@
+/*
+ * pcfm_b200.h — C ABI of libpcfm_b200.so: B200 (sm_100a) kernels for the point-cloud hot path of
+ * ruanjinchen/Point-Cloud-Flow-Matching (PVCNN point-voxel primitives + Chamfer-3D + approximate EMD).
+ *
+ * Boundary contract
+ *   - extern "C", plain pointers and sizes, no torch/ATen types.  Every pointer is a DEVICE pointer unless its
+ *     name ends in `_host`.  All tensors are dense, contiguous, fp32 / int32, laid out exactly as the
+ *     reference's tensors (PVCNN ops: channel-first [B,C,N] / [B,3,N]; Chamfer/EMD: [B,N,3]).
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Every entry point is
+ *     asynchronous, never synchronises the host, and launches only on `stream` (the reference launches
+ *     K1-K5, K11, K15-K20 on the legacy stream) so callers may CUDA-graph capture.
+ *   - Return value: 0 on success, otherwise a cudaError_t (positive) or PCFM_E_* (negative).
+ *   - Outputs are FULLY overwritten (no pre-zeroing needed) unless the comment says "accumulates".
+ *   - `workspace` is caller-owned scratch of at least pcfm_*_workspace(...) bytes, 256-byte aligned; it may
+ *     be reused by the next call on the same stream.
+ *   - Index arithmetic is 64-bit inside the kernels (the reference overflows int at B*C*r^3 >= 2^31).
+ *
+ * Each entry point cites the reference interface (file:line under /root/reference) it replaces.
+ */
+#ifndef PCFM_B200_H
+#define PCFM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PCFM_ABI_VERSION 1
+
+#define PCFM_E_BADARG   (-1)  /* NULL pointer / negative size / unsupported size */
+#define PCFM_E_WORKSPACE (-2) /* workspace too small */
+
+typedef void* pcfm_stream_t; /* cudaStream_t */
+
+/* Library / build info. */
+int pcfm_abi_version(void);
+/* Returns a static string such as "pcfm_b200 sm_100a nvcc 12.9". */
+const char* pcfm_build_info(void);
+/* Number of kernel launches issued by this library in the calling process since load (or last reset). */
+int64_t pcfm_launch_count(void);
+void pcfm_reset_launch_count(void);
+/* Tuning knob: "variant" selects alternative kernel implementations for A/B measurement.
+ * key: "devox_bwd" (0 = sorted-CSR gather [default], 1 = global RED atomics),
+ *      "vox_fwd"   (0 = sorted-CSR gather [default], 1 = global RED atomics),
+ *      "stage"     (0 = TMA bulk staging where aligned [default], 1 = plain ld/st staging). */
+int pcfm_set_option(const char* key, int value);
+
+/* ------------------------------------------------------------------------------------------------
+ * Voxelisation (third_party/pvcnn/modules/functional/src/voxelization/vox.cpp:17-43,54-76;
+ *               kernels vox.cu:18-34,48-72,86-110)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* avg_voxelize_forward (vox.cpp:17-43): features f32[B,C,N], coords i32[B,3,N] (already voxel integers in
+ * [0,r-1]) -> out f32[B,C,r^3], ind i32[B,N] (= x*r^2+y*r+z), cnt i32[B,r^3].
+ * out[b,c,v] = sum over points with ind==v of features*(1/cnt[v]); empty voxels are 0.
+ * The sum runs in ascending point order (one legal ordering of the reference's atomics) => deterministic. */
+size_t pcfm_avg_voxelize_forward_workspace(int b, int c, int n, int r);
+int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, int c, int n, int r,
+                              float* out, int* ind, int* cnt,
+                              void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* avg_voxelize_backward (vox.cpp:54-76): grad_y f32[B,C,S], ind i32[B,N], cnt i32[B,S] -> grad_x f32[B,C,N]
+ * grad_x[b,c,i] = grad_y[b,c,ind[i]] * (1/cnt[ind[i]]). */
+size_t pcfm_avg_voxelize_backward_workspace(int b, int c, int n, int s);
+int pcfm_avg_voxelize_backward(const float* grad_y, const int* ind, const int* cnt, int b, int c, int n, int s,
+                               float* grad_x, void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Trilinear devoxelisation (src/interpolate/trilinear_devox.cpp:18-55,67-91; kernels
+ *                           trilinear_devox.cu:21-105,119-162)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* trilinear_devoxelize_forward (trilinear_devox.cpp:18-55): coords f32[B,3,N] in [0,r-1],
+ * features f32[B,C,r^3] -> outs f32[B,C,N]; if is_training also inds i32[B,8,N], wgts f32[B,8,N]
+ * (corner order 000,001,010,011,100,101,110,111; hi offsets only where frac>0, trilinear_devox.cu:64-75).
+ * inds/wgts may be NULL when is_training==0. */
+int pcfm_trilinear_devoxelize_forward(const float* coords, const float* features, int b, int c, int n, int r,
+                                      int is_training, float* outs, int* inds, float* wgts,
+                                      pcfm_stream_t stream);
+
+/* trilinear_devoxelize_backward (trilinear_devox.cpp:67-91): grad_y f32[B,C,N], inds i32[B,8,N],
+ * wgts f32[B,8,N] -> grad_x f32[B,C,r^3];  grad_x[b,c,inds[b,k,i]] += wgts[b,k,i]*grad_y[b,c,i].
+ * Works for arbitrary inds in [0,r^3).  Deterministic (sorted segmented sums) in the default variant. */
+size_t pcfm_trilinear_devoxelize_backward_workspace(int b, int c, int n, int r);
+int pcfm_trilinear_devoxelize_backward(const float* grad_y, const int* inds, const float* wgts,
+                                       int b, int c, int n, int r, float* grad_x,
+                                       void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Ball query / grouping / gather / FPS / 3-NN  (src/ball_query, src/grouping, src/sampling,
+ *                                               src/interpolate/neighbor_interpolate.*)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* ball_query_forward (ball_query.cpp:6-30, ball_query.cu:19-50): centers f32[B,3,M], points f32[B,3,N]
+ * -> idx i32[B,M,U]: first U point indices (ascending) with d2 < radius^2 (strict, d2 evaluated as in the
+ * reference SASS: fma(dz,dz,fma(dx,dx,dy*dy)) on centre-point); remaining slots = first hit; no hit -> 0. */
+int pcfm_ball_query(const float* centers, const float* points, int b, int n, int m, float radius, int u,
+                    int* idx, pcfm_stream_t stream);
+
+/* grouping_forward (grouping.cpp:6-24): features f32[B,C,N], indices i32[B,M,U] -> out f32[B,C,M,U]. */
+int pcfm_grouping_forward(const float* features, const int* indices, int b, int c, int n, int m, int u,
+                          float* out, pcfm_stream_t stream);
+/* grouping_backward (grouping.cpp:26-44): grad_y f32[B,C,M,U], indices -> grad_x f32[B,C,N] (scatter-add). */
+size_t pcfm_grouping_backward_workspace(int b, int c, int n, int m, int u);
+int pcfm_grouping_backward(const float* grad_y, const int* indices, int b, int c, int n, int m, int u,
+                           float* grad_x, void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* gather_features_forward (sampling.cpp:6-24): features f32[B,C,N], indices i32[B,M] -> out f32[B,C,M]. */
+int pcfm_gather_features_forward(const float* features, const int* indices, int b, int c, int n, int m,
+                                 float* out, pcfm_stream_t stream);
+/* gather_features_backward (sampling.cpp:26-41): grad_y f32[B,C,M], indices -> grad_x f32[B,C,N]. */
+size_t pcfm_gather_features_backward_workspace(int b, int c, int n, int m);
+int pcfm_gather_features_backward(const float* grad_y, const int* indices, int b, int c, int n, int m,
+                                  float* grad_x, void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* furthest_point_sampling_forward (sampling.cpp:43-58, sampling.cu:86-167): coords f32[B,3,N] ->
+ * indices i32[B,M].  indices[0]=0; round j picks arg-max of the running min squared distance with the
+ * reference's tie-break (ties -> smallest k mod 512, then smallest k).  workspace: B*N floats. */
+size_t pcfm_furthest_point_sampling_workspace(int b, int n, int m);
+int pcfm_furthest_point_sampling(const float* coords, int b, int n, int m, int* indices,
+                                 void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* three_nearest_neighbors_interpolate_forward (neighbor_interpolate.cpp:6-40, .cu:20-116):
+ * points f32[B,3,N], centers f32[B,3,M], centers_features f32[B,C,M] ->
+ * out f32[B,C,N], idx i32[B,3,N], wgt f32[B,3,N]. */
+int pcfm_three_nn_interpolate_forward(const float* points, const float* centers, const float* centers_features,
+                                      int b, int c, int n, int m, float* out, int* idx, float* wgt,
+                                      pcfm_stream_t stream);
+/* three_nearest_neighbors_interpolate_backward (neighbor_interpolate.cpp:42-65, .cu:145-170):
+ * grad_y f32[B,C,N], idx i32[B,3,N], wgt f32[B,3,N] -> grad_x f32[B,C,M]. */
+size_t pcfm_three_nn_interpolate_backward_workspace(int b, int c, int n, int m);
+int pcfm_three_nn_interpolate_backward(const float* grad_y, const int* idx, const float* wgt,
+                                       int b, int c, int n, int m, float* grad_x,
+                                       void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Chamfer 3D (third_party/ChamferDistancePytorch/chamfer3D/chamfer_cuda.cpp:17-26,
+ *             chamfer3D.cu:12-154 forward, :155-195 backward)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* chamfer_3D.forward (chamfer_cuda.cpp:17-19): xyz1 f32[B,N,3], xyz2 f32[B,M,3] ->
+ * dist1 f32[B,N] (min_j squared distance), idx1 i32[B,N] (lowest-index arg-min), dist2 f32[B,M], idx2 i32[B,M].
+ * Distances are evaluated exactly as the reference SASS: d = fma(dz,dz,fma(dx,dx,dy*dy)) on (other - self). */
+int pcfm_chamfer3d_forward(const float* xyz1, const float* xyz2, int b, int n, int m,
+                           float* dist1, float* dist2, int* idx1, int* idx2, pcfm_stream_t stream);
+/* chamfer_3D.backward (chamfer_cuda.cpp:22-26): ACCUMULATES into gradxyz1 f32[B,N,3], gradxyz2 f32[B,M,3]
+ * (caller zeroes them, as dist_chamfer_3D.py:75-79 does). */
+int pcfm_chamfer3d_backward(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                            const int* idx1, const int* idx2, int b, int n, int m,
+                            float* gradxyz1, float* gradxyz2, pcfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Approximate EMD (third_party/PyTorchEMD/cuda/emd.cpp:23-27, emd_kernel.cu:24-396)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* approxmatch_forward (emd_kernel.cu:169-191): xyz1 f32[B,N,3], xyz2 f32[B,M,3] -> match f32[B,M,N].
+ * workspace: B*2*(N+M) floats (the reference's `temp`). */
+size_t pcfm_emd_approxmatch_workspace(int b, int n, int m);
+int pcfm_emd_approxmatch_forward(const float* xyz1, const float* xyz2, int b, int n, int m, float* match,
+                                 void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+/* matchcost_forward (emd_kernel.cu:255-277): -> cost f32[B] = sum_{k,l} |x1_k-x2_l|^2 * match[l,k]. */
+size_t pcfm_emd_matchcost_workspace(int b, int n, int m);
+int pcfm_emd_matchcost_forward(const float* xyz1, const float* xyz2, const float* match, int b, int n, int m,
+                               float* cost, void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+/* matchcost_backward (emd_kernel.cu:371-396): grad_cost f32[B] -> grad1 f32[B,N,3], grad2 f32[B,M,3]. */
+int pcfm_emd_matchcost_backward(const float* grad_cost, const float* xyz1, const float* xyz2, const float* match,
+                                int b, int n, int m, float* grad1, float* grad2, pcfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * All-pairs evaluation blocks (new capability used by the sharded MMD/COV/1-NNA harness; each entry is
+ * defined as the reference operator applied to the pair (S[i], R[j]) — SURVEY.md section 8(e)).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* cd[i,j] = mean_k dist1(S_i,R_j)[k] + mean_l dist2(S_i,R_j)[l]  with dist1/dist2 as pcfm_chamfer3d_forward.
+ * S f32[ns,N,3], R f32[nr,M,3] -> cd f32[ns,nr].  Each distance is evaluated once and feeds both minima. */
+int pcfm_chamfer3d_allpairs(const float* s, const float* r, int ns, int nr, int n, int m, float* cd,
+                            pcfm_stream_t stream);
+/* emd[i,j] = matchcost(approxmatch(S_i,R_j)) / N  (emd.py:48-50), never materialising `match`.
+ * workspace: see pcfm_emd_allpairs_workspace. */
+size_t pcfm_emd_allpairs_workspace(int ns, int nr, int n, int m);
+int pcfm_emd_allpairs(const float* s, const float* r, int ns, int nr, int n, int m, float* emd,
+                      void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-buffer convenience entry points (pageable or pinned HOST pointers; the copies run on `stream`
+ * inside the call and the call returns after the results are in the host buffers).
+ * ---------------------------------------------------------------------------------------------- */
+int pcfm_chamfer3d_forward_host(const float* xyz1_host, const float* xyz2_host, int b, int n, int m,
+                                float* dist1_host, float* dist2_host, int* idx1_host, int* idx2_host);
+int pcfm_avg_voxelize_forward_host(const float* features_host, const int* coords_host, int b, int c, int n, int r,
+                                   float* out_host, int* ind_host, int* cnt_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCFM_B200_H */

@@ -1,0 +1,279 @@
+// chamfer.cu — Chamfer-3D nearest neighbour (chamfer3D.cu:12-154), its gradient (:155-195) and the
+// all-pairs block kernel used by the sharded evaluation.
+//
+// fp32-ALU bound: every thread keeps RA "own" points in registers and streams the other
+// cloud from shared memory as broadcast LDS.128.  The distance is evaluated exactly as the reference's SASS
+// (sq3 on other-self), so minima are bit-identical; arg-min = lowest index (strict < in ascending order).
+#include "common.cuh"
+
+namespace pcfm {
+
+constexpr int kChThreads = 128;
+constexpr int kChChunk = 2048;  // points of the other cloud per shared-memory chunk (32 KB as float4)
+
+__device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); }
+
+// one direction: for every point of `a` ([B,n,3]) the nearest point of `o` ([B,m,3])
+template <int RA>
+__global__ void __launch_bounds__(kChThreads)
+    chamfer_nn_kernel(const float* __restrict__ a, const float* __restrict__ o, int n, int m,
+                      float* __restrict__ dist, int* __restrict__ idx) {
+  __shared__ float4 buf[kChChunk];
+  const int b = blockIdx.y;
+  const float* ab = a + (long long)b * n * 3;
+  const float* ob = o + (long long)b * m * 3;
+  const int row0 = blockIdx.x * (kChThreads * RA) + threadIdx.x;
+  float ax[RA], ay[RA], az[RA], best[RA];
+  int bk[RA];
+#pragma unroll
+  for (int r = 0; r < RA; ++r) {
+    const int i = row0 + r * kChThreads;
+    const bool v = i < n;
+    ax[r] = v ? ab[(long long)i * 3 + 0] : 0.f;
+    ay[r] = v ? ab[(long long)i * 3 + 1] : 0.f;
+    az[r] = v ? ab[(long long)i * 3 + 2] : 0.f;
+    best[r] = pos_inf();
+    bk[r] = 0;
+  }
+  for (int k2 = 0; k2 < m; k2 += kChChunk) {
+    const int len = min(kChChunk, m - k2);
+    const int len4 = (len + 3) & ~3;
+    __syncthreads();
+    for (int k = threadIdx.x; k < len4; k += kChThreads) {
+      float4 q;
+      if (k < len) {
+        const float* p = ob + (long long)(k2 + k) * 3;
+        q = make_float4(p[0], p[1], p[2], 0.f);
+      } else {
+        q = make_float4(pos_inf(), pos_inf(), pos_inf(), 0.f);  // padding: distance +inf, never a strict minimum
+      }
+      buf[k] = q;
+    }
+    __syncthreads();
+    for (int k = 0; k < len4; k += 4) {
+      const float4 q0 = buf[k], q1 = buf[k + 1], q2 = buf[k + 2], q3 = buf[k + 3];
+#pragma unroll
+      for (int r = 0; r < RA; ++r) {
+        const float d0 = sq3(q0.x - ax[r], q0.y - ay[r], q0.z - az[r]);
+        const float d1 = sq3(q1.x - ax[r], q1.y - ay[r], q1.z - az[r]);
+        const float d2 = sq3(q2.x - ax[r], q2.y - ay[r], q2.z - az[r]);
+        const float d3 = sq3(q3.x - ax[r], q3.y - ay[r], q3.z - az[r]);
+        const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+        if (m4 < best[r]) {  // strict: the first group of four that reaches the minimum wins
+          best[r] = m4;
+          bk[r] = k2 + k;
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RA; ++r) {
+    const int i = row0 + r * kChThreads;
+    if (i >= n) continue;
+    // lowest index inside the winning group of four: recompute the (bit-identical) distances
+    int bi = bk[r];
+    for (int t = 0; t < 4; ++t) {
+      const int k = bk[r] + t;
+      if (k >= m) break;
+      const float* p = ob + (long long)k * 3;
+      const float d = sq3(p[0] - ax[r], p[1] - ay[r], p[2] - az[r]);
+      if (d == best[r]) {
+        bi = k;
+        break;
+      }
+    }
+    dist[(long long)b * n + i] = best[r];
+    idx[(long long)b * n + i] = bi;
+  }
+}
+
+// gradient (chamfer3D.cu:155-174, both launches fused): accumulates into grad1 / grad2
+__global__ void __launch_bounds__(256)
+    chamfer_grad_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
+                        const float* __restrict__ gd1, const float* __restrict__ gd2,
+                        const int* __restrict__ idx1, const int* __restrict__ idx2, int n, int m,
+                        float* __restrict__ g1, float* __restrict__ g2) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* p1 = xyz1 + (long long)b * n * 3;
+  const float* p2 = xyz2 + (long long)b * m * 3;
+  float* o1 = g1 + (long long)b * n * 3;
+  float* o2 = g2 + (long long)b * m * 3;
+  if (j < n) {
+    const int j2 = min(max(idx1[(long long)b * n + j], 0), m - 1);
+    const float g = gd1[(long long)b * n + j] * 2;
+    const float dx = p1[j * 3LL + 0] - p2[j2 * 3LL + 0];
+    const float dy = p1[j * 3LL + 1] - p2[j2 * 3LL + 1];
+    const float dz = p1[j * 3LL + 2] - p2[j2 * 3LL + 2];
+    atomicAdd(o1 + j * 3LL + 0, __fmul_rn(g, dx));
+    atomicAdd(o1 + j * 3LL + 1, __fmul_rn(g, dy));
+    atomicAdd(o1 + j * 3LL + 2, __fmul_rn(g, dz));
+    atomicAdd(o2 + j2 * 3LL + 0, -__fmul_rn(g, dx));
+    atomicAdd(o2 + j2 * 3LL + 1, -__fmul_rn(g, dy));
+    atomicAdd(o2 + j2 * 3LL + 2, -__fmul_rn(g, dz));
+  }
+  if (j < m) {
+    const int j1 = min(max(idx2[(long long)b * m + j], 0), n - 1);
+    const float g = gd2[(long long)b * m + j] * 2;
+    const float dx = p2[j * 3LL + 0] - p1[j1 * 3LL + 0];
+    const float dy = p2[j * 3LL + 1] - p1[j1 * 3LL + 1];
+    const float dz = p2[j * 3LL + 2] - p1[j1 * 3LL + 2];
+    atomicAdd(o2 + j * 3LL + 0, __fmul_rn(g, dx));
+    atomicAdd(o2 + j * 3LL + 1, __fmul_rn(g, dy));
+    atomicAdd(o2 + j * 3LL + 2, __fmul_rn(g, dz));
+    atomicAdd(o1 + j1 * 3LL + 0, -__fmul_rn(g, dx));
+    atomicAdd(o1 + j1 * 3LL + 1, -__fmul_rn(g, dy));
+    atomicAdd(o1 + j1 * 3LL + 2, -__fmul_rn(g, dz));
+  }
+}
+
+// =================================================================================================
+// all-pairs Chamfer: one CTA per (S_i, R_j) cloud pair.  Each squared distance is evaluated ONCE and feeds
+// the row minimum (registers) and the column minimum (warp shuffle min, then one shared-memory atomicMin on
+// the float bit pattern per warp; non-negative floats order like unsigned ints).  No indices are needed for
+// the metric, so the inner loop is 3 FADD + FMUL + 2 FFMA + 2 FMNMX per pair of points.
+// =================================================================================================
+constexpr int kApThreads = 128;
+constexpr int kApRows = 16;  // own points per thread => 2048 rows per sweep
+constexpr int kApMaxM = 8192;
+
+__global__ void __launch_bounds__(kApThreads)
+    chamfer_allpairs_kernel(const float* __restrict__ s, const float* __restrict__ rr, int nr, int n, int m,
+                            float* __restrict__ cd) {
+  extern __shared__ __align__(16) unsigned char ap_smem[];
+  float4* col = (float4*)ap_smem;               // [m]
+  unsigned* colmin = (unsigned*)(col + m);      // [m]
+  __shared__ float red[kApThreads / 32];
+  const long long pair = blockIdx.x;
+  const int i = (int)(pair / nr), j = (int)(pair % nr);
+  const float* a = s + (long long)i * n * 3;
+  const float* o = rr + (long long)j * m * 3;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int k = threadIdx.x; k < m; k += kApThreads) {
+    const float* p = o + (long long)k * 3;
+    col[k] = make_float4(p[0], p[1], p[2], 0.f);
+    colmin[k] = 0x7f800000u;
+  }
+  __syncthreads();
+  float rowsum = 0.f;
+  for (int base = 0; base < n; base += kApThreads * kApRows) {
+    float ax[kApRows], ay[kApRows], az[kApRows], rmin[kApRows];
+#pragma unroll
+    for (int r = 0; r < kApRows; ++r) {
+      const int row = base + r * kApThreads + threadIdx.x;
+      const bool v = row < n;
+      // rows past the end sit at +inf: their distances are +inf (or NaN) and never lower a minimum
+      ax[r] = v ? a[(long long)row * 3 + 0] : pos_inf();
+      ay[r] = v ? a[(long long)row * 3 + 1] : pos_inf();
+      az[r] = v ? a[(long long)row * 3 + 2] : pos_inf();
+      rmin[r] = pos_inf();
+    }
+    for (int k = 0; k < m; ++k) {
+      const float4 q = col[k];
+      float cm = pos_inf();
+#pragma unroll
+      for (int r = 0; r < kApRows; ++r) {
+        const float d = sq3(q.x - ax[r], q.y - ay[r], q.z - az[r]);
+        rmin[r] = fminf(rmin[r], d);
+        cm = fminf(cm, d);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) cm = fminf(cm, __shfl_xor_sync(0xffffffffu, cm, off));
+      if (lane == 0) atomicMin(colmin + k, __float_as_uint(cm));
+    }
+#pragma unroll
+    for (int r = 0; r < kApRows; ++r) {
+      const int row = base + r * kApThreads + threadIdx.x;
+      if (row < n) rowsum += rmin[r];
+    }
+  }
+  __syncthreads();
+  float colsum = 0.f;
+  for (int k = threadIdx.x; k < m; k += kApThreads) colsum += __uint_as_float(colmin[k]);
+  rowsum = warp_sum(rowsum);
+  colsum = warp_sum(colsum);
+  __shared__ float red2[kApThreads / 32];
+  if (lane == 0) {
+    red[wid] = rowsum;
+    red2[wid] = colsum;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float rs = 0.f, cs = 0.f;
+    for (int w = 0; w < kApThreads / 32; ++w) {
+      rs += red[w];
+      cs += red2[w];
+    }
+    cd[pair] = rs / (float)n + cs / (float)m;
+  }
+}
+
+}  // namespace pcfm
+
+using namespace pcfm;
+
+extern "C" {
+
+int pcfm_chamfer3d_forward(const float* xyz1, const float* xyz2, int b, int n, int m, float* dist1,
+                           float* dist2, int* idx1, int* idx2, pcfm_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCFM_E_BADARG;
+  if (b == 0 || n == 0 || m == 0) return 0;  // the reference's loops do not execute: outputs untouched
+  if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int dir = 0; dir < 2; ++dir) {
+    const float* a = dir ? xyz2 : xyz1;
+    const float* o = dir ? xyz1 : xyz2;
+    const int na = dir ? m : n, no = dir ? n : m;
+    float* d = dir ? dist2 : dist1;
+    int* ix = dir ? idx2 : idx1;
+    const long long rows = (long long)na * b;
+    const long long want = 2LL * num_sms() * kChThreads;
+    if (rows >= want * 4) {
+      dim3 grid(cdiv(na, kChThreads * 4), b);
+      chamfer_nn_kernel<4><<<grid, kChThreads, 0, st>>>(a, o, na, no, d, ix);
+    } else if (rows >= want * 2) {
+      dim3 grid(cdiv(na, kChThreads * 2), b);
+      chamfer_nn_kernel<2><<<grid, kChThreads, 0, st>>>(a, o, na, no, d, ix);
+    } else {
+      dim3 grid(cdiv(na, kChThreads), b);
+      chamfer_nn_kernel<1><<<grid, kChThreads, 0, st>>>(a, o, na, no, d, ix);
+    }
+    PCFM_LAUNCHED();
+  }
+  return 0;
+}
+
+int pcfm_chamfer3d_backward(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                            const int* idx1, const int* idx2, int b, int n, int m, float* gradxyz1,
+                            float* gradxyz2, pcfm_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCFM_E_BADARG;
+  if (b == 0 || n == 0 || m == 0) return 0;
+  if (!xyz1 || !xyz2 || !graddist1 || !graddist2 || !idx1 || !idx2 || !gradxyz1 || !gradxyz2)
+    return PCFM_E_BADARG;
+  dim3 grid(cdiv(n > m ? n : m, 256), b);
+  chamfer_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(xyz1, xyz2, graddist1, graddist2, idx1, idx2, n,
+                                                              m, gradxyz1, gradxyz2);
+  PCFM_LAUNCHED();
+  return 0;
+}
+
+int pcfm_chamfer3d_allpairs(const float* s, const float* r, int ns, int nr, int n, int m, float* cd,
+                            pcfm_stream_t stream) {
+  if (ns < 0 || nr < 0 || n <= 0 || m <= 0 || m > kApMaxM) return PCFM_E_BADARG;
+  if ((long long)ns * nr > 0x7fffffffLL) return PCFM_E_BADARG;
+  if (ns == 0 || nr == 0) return 0;
+  if (!s || !r || !cd) return PCFM_E_BADARG;
+  static bool attr_set = false;
+  if (!attr_set) {
+    PCFM_CUDA(cudaFuncSetAttribute(chamfer_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   kApMaxM * 20));
+    attr_set = true;
+  }
+  const size_t smem = (size_t)m * 20;
+  chamfer_allpairs_kernel<<<(unsigned)((long long)ns * nr), kApThreads, smem, (cudaStream_t)stream>>>(
+      s, r, nr, n, m, cd);
+  PCFM_LAUNCHED();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,149 @@
+// common.cuh — shared device/host helpers for libpcfm_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/pcfm_b200.h"
+
+#define PCFM_STR2(x) #x
+#define PCFM_STR(x) PCFM_STR2(x)
+
+namespace pcfm {
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+extern int64_t g_launches;      // kernels launched by this library (pcfm_launch_count)
+extern int g_opt_devox_bwd;     // see pcfm_set_option
+extern int g_opt_vox_fwd;
+extern int g_opt_stage;
+extern int g_num_sms;           // cached SM count of the current device (148 on B200)
+int num_sms();
+
+#define PCFM_LAUNCHED()                                   \
+  do {                                                    \
+    ++::pcfm::g_launches;                                 \
+    cudaError_t e__ = cudaGetLastError();                 \
+    if (e__ != cudaSuccess) return (int)e__;              \
+  } while (0)
+
+#define PCFM_CUDA(x)                                      \
+  do {                                                    \
+    cudaError_t e__ = (x);                                \
+    if (e__ != cudaSuccess) return (int)e__;              \
+  } while (0)
+
+static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// bump allocator over the caller's workspace
+struct Workspace {
+  char* base;
+  size_t cap, off;
+  Workspace(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    size_t bytes = align256(count * sizeof(T));
+    if (off + bytes > cap || base == nullptr) { off = cap + 1; return nullptr; }
+    T* r = (T*)(base + off);
+    off += bytes;
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// device side
+// ---------------------------------------------------------------------------------------------
+// The reference's `dx*dx+dy*dy+dz*dz` is contracted by nvcc (default -fmad=true) into
+// FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.)  (SASS of chamfer3D.cu:35, ball_query.cu:38, sampling.cu:134,
+// neighbor_interpolate.cu:43).  Written with intrinsics so the order is fixed whatever the compiler does.
+__device__ __forceinline__ float sq3(float dx, float dy, float dz) {
+  return __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + 1-D TMA bulk copies (cp.async.bulk; SASS: UBLKCP) -----------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// make generic-proxy smem writes visible to the async proxy (before a bulk store / before TMA overwrites)
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a byte-count bug must surface as a trap (error code), never as a hung GPU box.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it) {
+    if (it > (1u << 24)) __trap();
+  }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(__cvta_generic_to_global(gmem_src)), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(
+                   __cvta_generic_to_global(gmem_dst)),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
+// Stage `count` floats from global into shared memory.  Called by ALL threads of the CTA.
+// Uses one elected thread issuing 1-D TMA bulk copies when src/dst are 16-byte aligned (tail by plain loads),
+// otherwise a plain coalesced copy.  `bar` is an initialised mbarrier (count 1), `phase` its current parity
+// (flipped by the caller after each use).  Ends with a __syncthreads(): data visible to every thread.
+constexpr uint32_t kBulkChunk = 32768;  // bytes per cp.async.bulk
+__device__ __forceinline__ void stage_floats(float* smem_dst, const float* gmem_src, int count, uint64_t* bar,
+                                             uint32_t phase, bool use_tma) {
+  const bool aligned = use_tma && ((((uintptr_t)gmem_src) & 15) == 0) && ((smem_u32(smem_dst) & 15) == 0);
+  int bulk_count = aligned ? (count & ~3) : 0;
+  if (bulk_count > 0) {
+    if (threadIdx.x == 0) {
+      uint32_t bytes = (uint32_t)bulk_count * 4u;
+      mbar_arrive_expect_tx(bar, bytes);
+      for (uint32_t off = 0; off < bytes; off += kBulkChunk) {
+        uint32_t sz = min(kBulkChunk, bytes - off);
+        bulk_g2s((char*)smem_dst + off, (const char*)gmem_src + off, sz, bar);
+      }
+    }
+  }
+  for (int i = bulk_count + threadIdx.x; i < count; i += blockDim.x) smem_dst[i] = __ldg(gmem_src + i);
+  if (bulk_count > 0) mbar_wait(bar, phase);
+  __syncthreads();
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace pcfm

@@ -1,0 +1,289 @@
+// pointops.cu — ball query, furthest point sampling, 3-nearest-neighbour search (+ interpolate forward).
+#include "rows.cuh"
+
+namespace pcfm {
+
+// =================================================================================================
+// ball query (ball_query.cu:19-50): one WARP per centre.  Points are streamed through shared memory in
+// tiles shared by the CTA's warps; 32 candidates are tested per step, hits are compacted with ballot +
+// prefix-popcount so the output keeps the reference's "first U in index order" rule, with early exit.
+// =================================================================================================
+constexpr int kBqWarps = 16;
+constexpr int kBqTile = 2048;
+
+__global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* __restrict__ centers,
+                                                                   const float* __restrict__ points, int n,
+                                                                   int m, float r2, int u,
+                                                                   int* __restrict__ out) {
+  __shared__ float px[kBqTile], py[kBqTile], pz[kBqTile];
+  const int b = blockIdx.y;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int j = blockIdx.x * kBqWarps + wid;
+  const bool valid = j < m;
+  const float* cb = centers + (long long)b * 3 * m;
+  const float* pb = points + (long long)b * 3 * n;
+  int* ob = out + ((long long)b * m + (valid ? j : 0)) * u;
+  float cx = 0.f, cy = 0.f, cz = 0.f;
+  if (valid) {
+    cx = cb[j];
+    cy = cb[(long long)j + m];
+    cz = cb[(long long)j + 2LL * m];
+  }
+  int cnt = 0, first = 0;
+  for (int base = 0; base < n; base += kBqTile) {
+    const int len = min(kBqTile, n - base);
+    for (int k = threadIdx.x; k < len; k += blockDim.x) {
+      px[k] = pb[base + k];
+      py[k] = pb[(long long)base + k + n];
+      pz[k] = pb[(long long)base + k + 2LL * n];
+    }
+    __syncthreads();
+    if (valid && cnt < u) {
+      for (int k0 = 0; k0 < len; k0 += 32) {
+        const int k = k0 + lane;
+        bool hit = false;
+        if (k < len) hit = sq3(cx - px[k], cy - py[k], cz - pz[k]) < r2;  // centre - point, strict <
+        const unsigned mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+          if (cnt == 0) first = base + k0 + __ffs(mask) - 1;
+          const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
+          if (hit && pos < u) ob[pos] = base + k;
+          cnt += __popc(mask);
+          if (cnt >= u) break;
+        }
+      }
+    }
+    const int done = (!valid || cnt >= u) ? 1 : 0;
+    if (__syncthreads_and(done)) break;
+  }
+  if (valid) {
+    // slots never reached keep the first hit (ball_query.cu:40-44); a centre without any hit stays 0
+    const int filled = min(cnt, u);
+    for (int v = filled + lane; v < u; v += 32) ob[v] = first;
+  }
+}
+
+// =================================================================================================
+// furthest point sampling (sampling.cu:86-167): one CTA per batch element, m dependent rounds.
+// Winner of a round = arg-max of the running min-distance with the reference's tie-break: the reference
+// runs 512 threads, thread t scans k = t, t+512, ... keeping the first strict maximum, then a pairwise tree
+// keeps the LEFT (lower thread id) entry on ties => ties go to the smallest (k mod 512), then the smallest k.
+// That order is encoded in a 64-bit key so any block size / reduction shape gives the same winner.
+// =================================================================================================
+__device__ __forceinline__ unsigned long long fps_key(float d, int k) {
+  const unsigned lo = ((511u - ((unsigned)k & 511u)) << 22) | (0x3FFFFFu - ((unsigned)k >> 9));
+  return ((unsigned long long)__float_as_uint(d) << 32) | lo;
+}
+__device__ __forceinline__ int fps_key_index(unsigned long long key) {
+  const unsigned lo = (unsigned)key;
+  return (int)(((0x3FFFFFu - (lo & 0x3FFFFFu)) << 9) | (511u - (lo >> 22)));
+}
+
+template <bool SMEM>
+__global__ void __launch_bounds__(1024, 1)
+    fps_kernel(const float* __restrict__ coords, int n, int m, float* __restrict__ dist_g,
+               int* __restrict__ indices) {
+  extern __shared__ __align__(16) float sm[];  // SMEM: x[n] y[n] z[n] d[n]
+  __shared__ unsigned long long wbest[32];
+  __shared__ int s_old;
+  if (m <= 0) return;
+  const int b = blockIdx.x;
+  const float* cb = coords + (long long)b * 3 * n;
+  float* dist = SMEM ? sm + 3 * (size_t)n : dist_g + (long long)b * n;
+  int* ib = indices + (long long)b * m;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    if (SMEM) {
+      sm[k] = cb[k];
+      sm[n + k] = cb[(long long)n + k];
+      sm[2 * n + k] = cb[2LL * n + k];
+    }
+    dist[k] = 1e38f;  // sampling.cpp:53
+  }
+  if (threadIdx.x == 0) ib[0] = 0;
+  __syncthreads();
+  int old = 0;
+  for (int j = 1; j < m; ++j) {
+    float x1, y1, z1;
+    if (SMEM) {
+      x1 = sm[old]; y1 = sm[n + old]; z1 = sm[2 * n + old];
+    } else {
+      x1 = cb[old]; y1 = cb[(long long)n + old]; z1 = cb[2LL * n + old];
+    }
+    unsigned long long best = 0ull;  // below every real key (distances are >= 0)
+    for (int k = threadIdx.x; k < n; k += blockDim.x) {
+      float x2, y2, z2;
+      if (SMEM) {
+        x2 = sm[k]; y2 = sm[n + k]; z2 = sm[2 * n + k];
+      } else {
+        x2 = cb[k]; y2 = cb[(long long)n + k]; z2 = cb[2LL * n + k];
+      }
+      const float td = dist[k];
+      const float d = sq3(x2 - x1, y2 - y1, z2 - z1);  // point - last selected
+      const float d2 = fminf(d, td);
+      if (d2 != td) dist[k] = d2;
+      const unsigned long long key = fps_key(d2, k);
+      best = key > best ? key : best;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
+      best = other > best ? other : best;
+    }
+    if (lane == 0) wbest[wid] = best;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long v = lane < nw ? wbest[lane] : 0ull;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+        v = other > v ? other : v;
+      }
+      if (lane == 0) {
+        const int w = v ? fps_key_index(v) : 0;
+        s_old = w;
+        ib[j] = w;
+      }
+    }
+    __syncthreads();
+    old = s_old;
+  }
+}
+
+// =================================================================================================
+// three nearest neighbours (neighbor_interpolate.cu:20-75): one thread per point, centres streamed
+// through shared memory; strict-< insertion keeps the earliest centre on ties.
+// =================================================================================================
+constexpr int kNnTile = 2048;
+
+__global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ points,
+                                                       const float* __restrict__ centers, int n, int m,
+                                                       float* __restrict__ weights, int* __restrict__ indices) {
+  __shared__ float cx[kNnTile], cy[kNnTile], cz[kNnTile];
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = j < n;
+  const float* pb = points + (long long)b * 3 * n;
+  const float* cb = centers + (long long)b * 3 * m;
+  float ux = 0.f, uy = 0.f, uz = 0.f;
+  if (valid) {
+    ux = pb[j];
+    uy = pb[(long long)j + n];
+    uz = pb[(long long)j + 2LL * n];
+  }
+  // the reference keeps the bests in double initialised to 1e40 (> FLT_MAX): +inf behaves identically
+  float best0 = __int_as_float(0x7f800000), best1 = best0, best2 = best0;
+  int i0 = 0, i1 = 0, i2 = 0;
+  for (int base = 0; base < m; base += kNnTile) {
+    const int len = min(kNnTile, m - base);
+    __syncthreads();
+    for (int k = threadIdx.x; k < len; k += blockDim.x) {
+      cx[k] = cb[base + k];
+      cy[k] = cb[(long long)base + k + m];
+      cz[k] = cb[(long long)base + k + 2LL * m];
+    }
+    __syncthreads();
+    if (valid) {
+      for (int k = 0; k < len; ++k) {
+        const float d = sq3(ux - cx[k], uy - cy[k], uz - cz[k]);
+        if (d < best2) {
+          best2 = d; i2 = base + k;
+          if (d < best1) {
+            best2 = best1; i2 = i1;
+            best1 = d; i1 = base + k;
+            if (d < best0) {
+              best1 = best0; i1 = i0;
+              best0 = d; i0 = base + k;
+            }
+          }
+        }
+      }
+    }
+  }
+  if (!valid) return;
+  best0 = fmaxf(fminf(1e10f, best0), 1e-10f);
+  best1 = fmaxf(fminf(1e10f, best1), 1e-10f);
+  best2 = fmaxf(fminf(1e10f, best2), 1e-10f);
+  const float d0d1 = __fmul_rn(best0, best1);
+  const float d0d2 = __fmul_rn(best0, best2);
+  const float d1d2 = __fmul_rn(best1, best2);
+  const float inv = __fdiv_rn(1.0f, __fadd_rn(__fadd_rn(d0d1, d0d2), d1d2));
+  float* wb = weights + (long long)b * 3 * n;
+  int* ib = indices + (long long)b * 3 * n;
+  wb[j] = __fmul_rn(d1d2, inv);
+  ib[j] = i0;
+  wb[(long long)j + n] = __fmul_rn(d0d2, inv);
+  ib[(long long)j + n] = i1;
+  wb[(long long)j + 2LL * n] = __fmul_rn(d0d1, inv);
+  ib[(long long)j + 2LL * n] = i2;
+}
+
+}  // namespace pcfm
+
+using namespace pcfm;
+
+extern "C" {
+
+int pcfm_ball_query(const float* centers, const float* points, int b, int n, int m, float radius, int u,
+                    int* idx, pcfm_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0 || u < 0) return PCFM_E_BADARG;
+  if (b == 0 || m == 0 || u == 0) return 0;
+  if (!centers || !idx || (n > 0 && !points)) return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n == 0) {
+    PCFM_CUDA(cudaMemsetAsync(idx, 0, (size_t)b * m * u * sizeof(int), st));
+    return 0;
+  }
+  dim3 grid(cdiv(m, kBqWarps), b);
+  ball_query_kernel<<<grid, kBqWarps * 32, 0, st>>>(centers, points, n, m, radius * radius, u, idx);
+  PCFM_LAUNCHED();
+  return 0;
+}
+
+size_t pcfm_furthest_point_sampling_workspace(int b, int n, int m) {
+  (void)m;
+  if (b <= 0 || n <= 0) return 256;
+  return align256((size_t)b * n * sizeof(float)) + 256;
+}
+
+int pcfm_furthest_point_sampling(const float* coords, int b, int n, int m, int* indices, void* workspace,
+                                 size_t workspace_bytes, pcfm_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCFM_E_BADARG;
+  if (b == 0 || m == 0) return 0;
+  if (!coords || !indices || n == 0) return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = (size_t)n * 4 * sizeof(float);
+  if (smem <= (size_t)kMaxStageFloats * sizeof(float)) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      PCFM_CUDA(cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(kMaxStageFloats * sizeof(float))));
+      attr_set = true;
+    }
+    fps_kernel<true><<<b, 1024, smem, st>>>(coords, n, m, nullptr, indices);
+  } else {
+    Workspace ws(workspace, workspace_bytes);
+    float* dist = ws.take<float>((size_t)b * n);
+    if (!ws.ok()) return PCFM_E_WORKSPACE;
+    fps_kernel<false><<<b, 1024, 0, st>>>(coords, n, m, dist, indices);
+  }
+  PCFM_LAUNCHED();
+  return 0;
+}
+
+int pcfm_three_nn_interpolate_forward(const float* points, const float* centers, const float* centers_features,
+                                      int b, int c, int n, int m, float* out, int* idx, float* wgt,
+                                      pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || m < 0) return PCFM_E_BADARG;
+  if (b == 0 || n == 0) return 0;
+  if (!points || !idx || !wgt || (m > 0 && !centers)) return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(cdiv(n, 256), b);
+  three_nn_kernel<<<grid, 256, 0, st>>>(points, centers, n, m, wgt, idx);
+  PCFM_LAUNCHED();
+  if (c == 0) return 0;
+  if (!centers_features || !out || m == 0) return PCFM_E_BADARG;
+  return launch_row_gather(3, centers_features, idx, wgt, out, b, c, m, n, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,419 @@
+// rows.cu — row engines + the entry points built directly on them:
+//   avg_voxelize fwd/bwd, grouping fwd/bwd, gather fwd/bwd, 3-NN interpolate bwd, trilinear devoxelize bwd.
+#include "rows.cuh"
+
+namespace pcfm {
+
+// =================================================================================================
+// row_segsum: grid (C, B), 1024 threads, one thread per output element, segment walked in plan order.
+// =================================================================================================
+template <int MODE, bool ROW_SMEM>
+__global__ void __launch_bounds__(1024, 1)
+    row_segsum_kernel(const float* __restrict__ src, const int* __restrict__ start,
+                      const int* __restrict__ ssrc, const float* __restrict__ sw, float* __restrict__ out,
+                      int C, int S, int T, int E, int use_tma) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar;
+  const int c = blockIdx.x, b = blockIdx.y;
+  const float* row_g = src + ((long long)b * C + c) * S;
+  if (ROW_SMEM) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    stage_floats(smem, row_g, S, &bar, 0, use_tma != 0);
+  }
+  const int* st = start + (long long)b * (T + 1);
+  const int* ss = ssrc + (long long)b * E;
+  const float* wv = (MODE == SEG_WEIGHTED) ? sw + (long long)b * E : nullptr;
+  float* o = out + ((long long)b * C + c) * T;
+  for (int t = threadIdx.x; t < T; t += blockDim.x) {
+    const int s0 = st[t], s1 = st[t + 1];
+    float acc = 0.f;
+    if (s1 > s0) {
+      float rcp = 1.f;
+      if (MODE == SEG_MEAN) rcp = __frcp_rn((float)(s1 - s0));  // == (float)(1.0/(float)cnt), vox.cu:65
+      for (int j = s0; j < s1; ++j) {
+        const int si = ss[j];
+        const float f = ROW_SMEM ? smem[si] : __ldg(row_g + si);
+        // the reference rounds the product, then adds it with an atomic (vox.cu:67, trilinear_devox.cu:152):
+        // keep product and sum as two roundings so a one-edge segment is bit-identical.
+        if (MODE == SEG_MEAN) acc = __fadd_rn(acc, __fmul_rn(f, rcp));
+        else if (MODE == SEG_WEIGHTED) acc = __fadd_rn(acc, __fmul_rn(wv[j], f));
+        else acc = __fadd_rn(acc, f);
+      }
+    }
+    o[t] = acc;
+  }
+}
+
+template <int MODE, bool ROW_SMEM>
+static int launch_segsum_t(const float* src, const CsrPlan& plan, float* out, int b, int c, int s, int t,
+                           int e, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = row_segsum_kernel<MODE, ROW_SMEM>;
+  const size_t smem = ROW_SMEM ? (size_t)s * sizeof(float) : 0;
+  if (!attr_set) {
+    PCFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kMaxStageFloats * sizeof(float))));
+    attr_set = true;
+  }
+  dim3 grid(c, b);
+  kern<<<grid, 1024, smem, st>>>(src, plan.start, plan.ssrc, plan.sw, out, c, s, t, e, g_opt_stage == 0);
+  PCFM_LAUNCHED();
+  return 0;
+}
+
+int launch_row_segsum(SegMode mode, const float* src, const CsrPlan& plan, float* out, int b, int c, int s,
+                      int t, int e, cudaStream_t st) {
+  if (b <= 0 || c <= 0 || t <= 0) return 0;
+  const bool in_smem = s <= kMaxStageFloats;
+  switch (mode) {
+    case SEG_WEIGHTED:
+      return in_smem ? launch_segsum_t<SEG_WEIGHTED, true>(src, plan, out, b, c, s, t, e, st)
+                     : launch_segsum_t<SEG_WEIGHTED, false>(src, plan, out, b, c, s, t, e, st);
+    case SEG_UNIT:
+      return in_smem ? launch_segsum_t<SEG_UNIT, true>(src, plan, out, b, c, s, t, e, st)
+                     : launch_segsum_t<SEG_UNIT, false>(src, plan, out, b, c, s, t, e, st);
+    default:
+      return in_smem ? launch_segsum_t<SEG_MEAN, true>(src, plan, out, b, c, s, t, e, st)
+                     : launch_segsum_t<SEG_MEAN, false>(src, plan, out, b, c, s, t, e, st);
+  }
+}
+
+// =================================================================================================
+// row_gather: grid (C/G, B), 1024 threads; G consecutive channel planes staged per CTA so the index /
+// weight stream is read once per G channels.
+// =================================================================================================
+template <int K, int G, bool PLANE_SMEM, bool HAS_W>
+__global__ void __launch_bounds__(1024, 1)
+    row_gather_kernel(const float* __restrict__ planes, const int* __restrict__ idx,
+                      const float* __restrict__ w, float* __restrict__ out, int C, int P, int J, int use_tma) {
+  extern __shared__ __align__(128) float smem[];
+  __shared__ uint64_t bar;
+  const int c0 = blockIdx.x * G, b = blockIdx.y;
+  const float* pg = planes + ((long long)b * C + c0) * P;
+  if (PLANE_SMEM) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+    __syncthreads();
+    stage_floats(smem, pg, G * P, &bar, 0, use_tma != 0);
+  }
+  const int* ib = idx + (long long)b * K * J;
+  const float* wb = HAS_W ? w + (long long)b * K * J : nullptr;
+  float* ob = out + ((long long)b * C + c0) * J;
+  const unsigned pmax = (unsigned)(P - 1);
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    unsigned id[K];
+    float wk[K];
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      id[k] = min((unsigned)ib[(long long)k * J + j], pmax);  // memory safety only; valid indices unchanged
+      wk[k] = HAS_W ? wb[(long long)k * J + j] : 1.f;
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float f[K];
+#pragma unroll
+      for (int k = 0; k < K; ++k) f[k] = PLANE_SMEM ? smem[g * P + id[k]] : __ldg(pg + (long long)g * P + id[k]);
+      float acc;
+      if (K == 1) {
+        acc = HAS_W ? __fmul_rn(f[0], wk[0]) : f[0];
+      } else {
+        acc = f[0] * wk[0];
+#pragma unroll
+        for (int k = 1; k < K; ++k) acc = fmaf(f[k], wk[k], acc);
+      }
+      ob[(long long)g * J + j] = acc;
+    }
+  }
+}
+
+template <int K, int G, bool PLANE_SMEM, bool HAS_W>
+static int launch_gather_t(const float* planes, const int* idx, const float* w, float* out, int b, int c,
+                           int p, int j, cudaStream_t st) {
+  static bool attr_set = false;
+  auto kern = row_gather_kernel<K, G, PLANE_SMEM, HAS_W>;
+  const size_t smem = PLANE_SMEM ? (size_t)G * p * sizeof(float) : 0;
+  if (!attr_set) {
+    PCFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)(kMaxStageFloats * sizeof(float))));
+    attr_set = true;
+  }
+  dim3 grid(c / G, b);
+  kern<<<grid, 1024, smem, st>>>(planes, idx, w, out, c, p, j, g_opt_stage == 0);
+  PCFM_LAUNCHED();
+  return 0;
+}
+
+// channels per CTA: as many as fit in ~96 KB while keeping >= 2 CTAs per SM in flight
+int pick_group(int b, int c, int p) {
+  if (p > kMaxStageFloats) return 0;  // plane does not fit: read through L2
+  int g = 8;
+  while (g > 1 && (c % g != 0 || (long long)g * p * 4 > 98304 || (long long)(c / g) * b < 2LL * num_sms()))
+    g >>= 1;
+  return g;
+}
+
+template <int K, bool HAS_W>
+static int launch_gather_k(const float* planes, const int* idx, const float* w, float* out, int b, int c,
+                           int p, int j, cudaStream_t st) {
+  switch (pick_group(b, c, p)) {
+    case 0: return launch_gather_t<K, 1, false, HAS_W>(planes, idx, w, out, b, c, p, j, st);
+    case 8: return launch_gather_t<K, 8, true, HAS_W>(planes, idx, w, out, b, c, p, j, st);
+    case 4: return launch_gather_t<K, 4, true, HAS_W>(planes, idx, w, out, b, c, p, j, st);
+    case 2: return launch_gather_t<K, 2, true, HAS_W>(planes, idx, w, out, b, c, p, j, st);
+    default: return launch_gather_t<K, 1, true, HAS_W>(planes, idx, w, out, b, c, p, j, st);
+  }
+}
+
+int launch_row_gather(int k, const float* planes, const int* idx, const float* w, float* out, int b, int c,
+                      int p, int j, cudaStream_t st) {
+  if (b <= 0 || c <= 0 || j <= 0) return 0;
+  if (p <= 0) return PCFM_E_BADARG;
+  if (k == 1) return w ? launch_gather_k<1, true>(planes, idx, w, out, b, c, p, j, st)
+                       : launch_gather_k<1, false>(planes, idx, nullptr, out, b, c, p, j, st);
+  if (k == 3 && w) return launch_gather_k<3, true>(planes, idx, w, out, b, c, p, j, st);
+  return PCFM_E_BADARG;
+}
+
+// =================================================================================================
+// small helper kernels
+// =================================================================================================
+// rcp[b,i] = 1/cnt[b,ind[b,i]]  (0 when the count is not positive: the reference skips such points, vox.cu:103)
+__global__ void __launch_bounds__(256) point_rcp_kernel(const int* __restrict__ ind,
+                                                        const int* __restrict__ cnt, int n, int s,
+                                                        float* __restrict__ rcp) {
+  const int b = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = ind[(long long)b * n + i];
+  int k = 0;
+  if (v >= 0 && v < s) k = cnt[(long long)b * s + v];
+  rcp[(long long)b * n + i] = k > 0 ? __frcp_rn((float)k) : 0.f;
+}
+
+// A/B variant: the reference's formulation (global fp32 RED per point-channel) on a full grid.
+__global__ void __launch_bounds__(256) vox_scatter_atomic_kernel(const float* __restrict__ feat,
+                                                                 const int* __restrict__ ind,
+                                                                 const int* __restrict__ cnt, int C, int n,
+                                                                 int s, float* __restrict__ out) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = ind[(long long)b * n + i];
+  if (v < 0 || v >= s) return;
+  const int k = cnt[(long long)b * s + v];
+  if (k <= 0) return;
+  const float f = feat[((long long)b * C + c) * n + i];
+  atomicAdd(out + ((long long)b * C + c) * s + v, __fmul_rn(f, __frcp_rn((float)k)));
+}
+
+__global__ void __launch_bounds__(256) devox_scatter_atomic_kernel(const float* __restrict__ grad_y,
+                                                                   const int* __restrict__ inds,
+                                                                   const float* __restrict__ wgts, int C,
+                                                                   int n, int s, float* __restrict__ grad_x) {
+  const int b = blockIdx.z, c = blockIdx.y;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float g = grad_y[((long long)b * C + c) * n + i];
+  float* gx = grad_x + ((long long)b * C + c) * s;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int v = inds[((long long)b * 8 + k) * n + i];
+    const float w = wgts[((long long)b * 8 + k) * n + i];
+    if (v >= 0 && v < s) atomicAdd(gx + v, __fmul_rn(w, g));
+  }
+}
+
+}  // namespace pcfm
+
+using namespace pcfm;
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// avg_voxelize
+// ---------------------------------------------------------------------------------------------
+size_t pcfm_avg_voxelize_forward_workspace(int b, int c, int n, int r) {
+  (void)c;
+  if (b <= 0 || n < 0 || r <= 0) return 0;
+  return csr_workspace_bytes(b, n, (long long)r * r * r, false) + 256;
+}
+
+int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, int c, int n, int r, float* out,
+                              int* ind, int* cnt, void* workspace, size_t workspace_bytes,
+                              pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || r <= 0 || (long long)r * r * r > 0x7fffffffLL) return PCFM_E_BADARG;
+  if (b == 0) return 0;
+  if (!coords || !ind || !cnt || (c > 0 && (!features || !out))) return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int s = r * r * r;
+  Workspace ws(workspace, workspace_bytes);
+  CsrPlan plan;
+  int rc = csr_build(nullptr, coords, r, ind, nullptr, b, n, s, n > 0 ? n : 1, cnt, &plan, &ws, st);
+  if (rc) return rc;
+  if (c == 0) return 0;
+  if (g_opt_vox_fwd == 1) {
+    PCFM_CUDA(cudaMemsetAsync(out, 0, (size_t)b * c * s * sizeof(float), st));
+    if (n > 0) {
+      dim3 grid(cdiv(n, 256), c, b);
+      vox_scatter_atomic_kernel<<<grid, 256, 0, st>>>(features, ind, cnt, c, n, s, out);
+      PCFM_LAUNCHED();
+    }
+    return 0;
+  }
+  return launch_row_segsum(SEG_MEAN, features, plan, out, b, c, n, s, n, st);
+}
+
+size_t pcfm_avg_voxelize_backward_workspace(int b, int c, int n, int s) {
+  (void)c; (void)s;
+  if (b <= 0 || n <= 0) return 256;
+  return align256((size_t)b * n * sizeof(float)) + 256;
+}
+
+int pcfm_avg_voxelize_backward(const float* grad_y, const int* ind, const int* cnt, int b, int c, int n, int s,
+                               float* grad_x, void* workspace, size_t workspace_bytes, pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || s <= 0) return PCFM_E_BADARG;
+  if (b == 0 || c == 0 || n == 0) return 0;
+  if (!grad_y || !ind || !cnt || !grad_x) return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  float* rcp = ws.take<float>((size_t)b * n);
+  if (!ws.ok()) return PCFM_E_WORKSPACE;
+  dim3 grid(cdiv(n, 256), b);
+  point_rcp_kernel<<<grid, 256, 0, st>>>(ind, cnt, n, s, rcp);
+  PCFM_LAUNCHED();
+  return launch_row_gather(1, grad_y, ind, rcp, grad_x, b, c, s, n, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// trilinear_devoxelize backward (generic: arbitrary inds / wgts)
+// ---------------------------------------------------------------------------------------------
+size_t pcfm_trilinear_devoxelize_backward_workspace(int b, int c, int n, int r) {
+  (void)c;
+  if (b <= 0 || n < 0 || r <= 0) return 0;
+  const long long s = (long long)r * r * r;
+  return csr_workspace_bytes(b, 8LL * n, s, true) + align256((size_t)b * s * sizeof(int)) + 256;
+}
+
+int pcfm_trilinear_devoxelize_backward(const float* grad_y, const int* inds, const float* wgts, int b, int c,
+                                       int n, int r, float* grad_x, void* workspace, size_t workspace_bytes,
+                                       pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || r <= 0 || (long long)r * r * r > 0x7fffffffLL || 8LL * n > 0x7fffffffLL)
+    return PCFM_E_BADARG;
+  if (b == 0 || c == 0) return 0;
+  if (!grad_x || (n > 0 && (!grad_y || !inds || !wgts))) return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int s = r * r * r;
+  if (g_opt_devox_bwd == 1 || n == 0) {
+    PCFM_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)b * c * s * sizeof(float), st));
+    if (n > 0) {
+      dim3 grid(cdiv(n, 256), c, b);
+      devox_scatter_atomic_kernel<<<grid, 256, 0, st>>>(grad_y, inds, wgts, c, n, s, grad_x);
+      PCFM_LAUNCHED();
+    }
+    return 0;
+  }
+  Workspace ws(workspace, workspace_bytes);
+  int* cnt = ws.take<int>((size_t)b * s);
+  if (!ws.ok()) return PCFM_E_WORKSPACE;
+  CsrPlan plan;
+  int rc = csr_build(inds, nullptr, 0, nullptr, wgts, b, 8 * n, s, n, cnt, &plan, &ws, st);
+  if (rc) return rc;
+  return launch_row_segsum(SEG_WEIGHTED, grad_y, plan, grad_x, b, c, n, s, 8 * n, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// grouping / gather
+// ---------------------------------------------------------------------------------------------
+int pcfm_grouping_forward(const float* features, const int* indices, int b, int c, int n, int m, int u,
+                          float* out, pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || m < 0 || u < 0 || (long long)m * u > 0x7fffffffLL) return PCFM_E_BADARG;
+  if (b == 0 || c == 0 || m == 0 || u == 0) return 0;
+  if (!features || !indices || !out || n == 0) return PCFM_E_BADARG;
+  return launch_row_gather(1, features, indices, nullptr, out, b, c, n, m * u, (cudaStream_t)stream);
+}
+
+static size_t scatter_ws(int b, long long e, long long t) {
+  return csr_workspace_bytes(b, e, t, false) + align256((size_t)b * t * sizeof(int)) + 256;
+}
+
+static int scatter_unit(const float* grad_y, const int* indices, int b, int c, int t, int e, float* grad_x,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  Workspace ws(workspace, workspace_bytes);
+  int* cnt = ws.take<int>((size_t)b * t);
+  if (!ws.ok()) return PCFM_E_WORKSPACE;
+  CsrPlan plan;
+  int rc = csr_build(indices, nullptr, 0, nullptr, nullptr, b, e, t, e > 0 ? e : 1, cnt, &plan, &ws, st);
+  if (rc) return rc;
+  return launch_row_segsum(SEG_UNIT, grad_y, plan, grad_x, b, c, e, t, e, st);
+}
+
+size_t pcfm_grouping_backward_workspace(int b, int c, int n, int m, int u) {
+  (void)c;
+  if (b <= 0 || n <= 0) return 256;
+  return scatter_ws(b, (long long)m * u, n);
+}
+
+int pcfm_grouping_backward(const float* grad_y, const int* indices, int b, int c, int n, int m, int u,
+                           float* grad_x, void* workspace, size_t workspace_bytes, pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || m < 0 || u < 0 || (long long)m * u > 0x7fffffffLL) return PCFM_E_BADARG;
+  if (b == 0 || c == 0 || n == 0) return 0;
+  if (!grad_x || ((long long)m * u > 0 && (!grad_y || !indices))) return PCFM_E_BADARG;
+  return scatter_unit(grad_y, indices, b, c, n, m * u, grad_x, workspace, workspace_bytes,
+                      (cudaStream_t)stream);
+}
+
+int pcfm_gather_features_forward(const float* features, const int* indices, int b, int c, int n, int m,
+                                 float* out, pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || m < 0) return PCFM_E_BADARG;
+  if (b == 0 || c == 0 || m == 0) return 0;
+  if (!features || !indices || !out || n == 0) return PCFM_E_BADARG;
+  return launch_row_gather(1, features, indices, nullptr, out, b, c, n, m, (cudaStream_t)stream);
+}
+
+size_t pcfm_gather_features_backward_workspace(int b, int c, int n, int m) {
+  (void)c;
+  if (b <= 0 || n <= 0) return 256;
+  return scatter_ws(b, m, n);
+}
+
+int pcfm_gather_features_backward(const float* grad_y, const int* indices, int b, int c, int n, int m,
+                                  float* grad_x, void* workspace, size_t workspace_bytes,
+                                  pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || m < 0) return PCFM_E_BADARG;
+  if (b == 0 || c == 0 || n == 0) return 0;
+  if (!grad_x || (m > 0 && (!grad_y || !indices))) return PCFM_E_BADARG;
+  return scatter_unit(grad_y, indices, b, c, n, m, grad_x, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------------------------------
+// 3-NN interpolate backward
+// ---------------------------------------------------------------------------------------------
+size_t pcfm_three_nn_interpolate_backward_workspace(int b, int c, int n, int m) {
+  (void)c;
+  if (b <= 0 || m <= 0) return 256;
+  return csr_workspace_bytes(b, 3LL * n, m, true) + align256((size_t)b * m * sizeof(int)) + 256;
+}
+
+int pcfm_three_nn_interpolate_backward(const float* grad_y, const int* idx, const float* wgt, int b, int c,
+                                       int n, int m, float* grad_x, void* workspace, size_t workspace_bytes,
+                                       pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || m < 0 || 3LL * n > 0x7fffffffLL) return PCFM_E_BADARG;
+  if (b == 0 || c == 0 || m == 0) return 0;
+  if (!grad_x || (n > 0 && (!grad_y || !idx || !wgt))) return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  int* cnt = ws.take<int>((size_t)b * m);
+  if (!ws.ok()) return PCFM_E_WORKSPACE;
+  CsrPlan plan;
+  int rc = csr_build(idx, nullptr, 0, nullptr, wgt, b, 3 * n, m, n > 0 ? n : 1, cnt, &plan, &ws, st);
+  if (rc) return rc;
+  return launch_row_segsum(SEG_WEIGHTED, grad_y, plan, grad_x, b, c, n, m, 3 * n, st);
+}
+
+}  // extern "C"

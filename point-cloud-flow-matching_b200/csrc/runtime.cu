@@ -1,0 +1,45 @@
+// runtime.cu — library globals: options, launch counter, build info.
+#include <string.h>
+
+#include "common.cuh"
+
+namespace pcfm {
+int64_t g_launches = 0;
+int g_opt_devox_bwd = 0;
+int g_opt_vox_fwd = 0;
+int g_opt_stage = 0;
+int g_num_sms = 0;
+
+int num_sms() {
+  if (g_num_sms <= 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      g_num_sms = n;
+    else
+      g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+}  // namespace pcfm
+
+extern "C" {
+
+int pcfm_abi_version(void) { return PCFM_ABI_VERSION; }
+
+const char* pcfm_build_info(void) {
+  return "pcfm_b200 abi1 sm_100a nvcc " PCFM_STR(__CUDACC_VER_MAJOR__) "." PCFM_STR(__CUDACC_VER_MINOR__);
+}
+
+int64_t pcfm_launch_count(void) { return pcfm::g_launches; }
+void pcfm_reset_launch_count(void) { pcfm::g_launches = 0; }
+
+int pcfm_set_option(const char* key, int value) {
+  if (!key) return PCFM_E_BADARG;
+  if (!strcmp(key, "devox_bwd")) { pcfm::g_opt_devox_bwd = value; return 0; }
+  if (!strcmp(key, "vox_fwd")) { pcfm::g_opt_vox_fwd = value; return 0; }
+  if (!strcmp(key, "stage")) { pcfm::g_opt_stage = value; return 0; }
+  return PCFM_E_BADARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,96 @@
+"""ctypes binding of libpcfm_b200.so.  Every symbol declared in include/pcfm_b200.h is bound here."""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libpcfm_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} is missing: build it with `python __graft_entry__.py build` "
+        "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU / PyTorch fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+_p = ctypes.c_void_p
+_i = ctypes.c_int
+_f = ctypes.c_float
+_sz = ctypes.c_size_t
+
+# name -> (restype, argtypes); mirrors include/pcfm_b200.h one to one
+SIGNATURES = {
+    "pcfm_abi_version": (_i, []),
+    "pcfm_build_info": (ctypes.c_char_p, []),
+    "pcfm_launch_count": (ctypes.c_int64, []),
+    "pcfm_reset_launch_count": (None, []),
+    "pcfm_set_option": (_i, [ctypes.c_char_p, _i]),
+    "pcfm_avg_voxelize_forward_workspace": (_sz, [_i, _i, _i, _i]),
+    "pcfm_avg_voxelize_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p]),
+    "pcfm_avg_voxelize_backward_workspace": (_sz, [_i, _i, _i, _i]),
+    "pcfm_avg_voxelize_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_trilinear_devoxelize_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "pcfm_trilinear_devoxelize_backward_workspace": (_sz, [_i, _i, _i, _i]),
+    "pcfm_trilinear_devoxelize_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_ball_query": (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _p]),
+    "pcfm_grouping_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "pcfm_grouping_backward_workspace": (_sz, [_i, _i, _i, _i, _i]),
+    "pcfm_grouping_backward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_gather_features_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "pcfm_gather_features_backward_workspace": (_sz, [_i, _i, _i, _i]),
+    "pcfm_gather_features_backward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_furthest_point_sampling_workspace": (_sz, [_i, _i, _i]),
+    "pcfm_furthest_point_sampling": (_i, [_p, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_three_nn_interpolate_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "pcfm_three_nn_interpolate_backward_workspace": (_sz, [_i, _i, _i, _i]),
+    "pcfm_three_nn_interpolate_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_chamfer3d_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "pcfm_chamfer3d_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "pcfm_emd_approxmatch_workspace": (_sz, [_i, _i, _i]),
+    "pcfm_emd_approxmatch_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_emd_matchcost_workspace": (_sz, [_i, _i, _i]),
+    "pcfm_emd_matchcost_forward": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_emd_matchcost_backward": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "pcfm_chamfer3d_allpairs": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "pcfm_emd_allpairs_workspace": (_sz, [_i, _i, _i, _i]),
+    "pcfm_emd_allpairs": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_chamfer3d_forward_host": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "pcfm_avg_voxelize_forward_host": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+}
+
+for _name, (_res, _args) in SIGNATURES.items():
+    _fn = getattr(lib, _name)  # AttributeError here == the library does not match the header
+    _fn.restype = _res
+    _fn.argtypes = _args
+
+if lib.pcfm_abi_version() != 1:
+    raise ImportError(f"{LIB_PATH}: ABI version {lib.pcfm_abi_version()} != 1")
+
+
+class PcfmError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc == 0:
+        return
+    if rc == -1:
+        raise PcfmError(f"{what}: bad argument (PCFM_E_BADARG)")
+    if rc == -2:
+        raise PcfmError(f"{what}: workspace too small (PCFM_E_WORKSPACE)")
+    raise PcfmError(f"{what}: CUDA error {rc}")
+
+
+def launch_count():
+    return int(lib.pcfm_launch_count())
+
+
+def reset_launch_count():
+    lib.pcfm_reset_launch_count()
+
+
+def set_option(key, value):
+    check(lib.pcfm_set_option(key.encode(), int(value)), f"pcfm_set_option({key})")
+
+
+def build_info():
+    return lib.pcfm_build_info().decode()

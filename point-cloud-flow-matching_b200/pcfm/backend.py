@@ -1,0 +1,370 @@
+"""Drop-in replacements for the reference's three pybind11 extension modules, on top of the C ABI.
+
+    pvcnn   <->  `_pvcnn_backend`   third_party/pvcnn/modules/functional/src/bindings.cpp:10-37
+    chamfer <->  `chamfer_3D`       third_party/ChamferDistancePytorch/chamfer3D/chamfer_cuda.cpp:30-33
+    emd     <->  `emd_ext`          third_party/PyTorchEMD/cuda/emd.cpp:23-27
+
+Same function names, argument order, return structure and error behaviour (argument checks raise
+RuntimeError exactly where the reference's TORCH_CHECKs do, utils.hpp:7-18).  torch is used for device
+memory and the current stream only; all arithmetic happens in libpcfm_b200.so.
+"""
+import torch
+
+from . import _lib
+from ._lib import lib, check
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t):
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _ws(nbytes, device):
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+def _check_cuda(x, name):
+    if not x.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _check_contig(x, name):
+    if not x.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+
+
+def _check_float(x, name):
+    if x.dtype != torch.float32:
+        raise RuntimeError(f"{name} must be a float tensor")
+
+
+def _check_int(x, name):
+    if x.dtype != torch.int32:
+        raise RuntimeError(f"{name} must be an int tensor")
+
+
+def _chk(x, name, kind):
+    _check_cuda(x, name)
+    _check_contig(x, name)
+    (_check_float if kind == "f" else _check_int)(x, name)
+
+
+class _PvcnnBackend:
+    """`_pvcnn_backend` (bindings.cpp:10-37)."""
+
+    # ---- voxelization (vox.cpp:17-43, 54-76) ----
+    @staticmethod
+    def avg_voxelize_forward(features, coords, resolution):
+        _chk(features, "features", "f")
+        _chk(coords, "coords", "i")
+        b, c, n = features.shape
+        r = int(resolution)
+        s = r * r * r
+        dev = features.device
+        out = torch.empty((b, c, s), dtype=torch.float32, device=dev)
+        ind = torch.empty((b, n), dtype=torch.int32, device=dev)
+        cnt = torch.empty((b, s), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            nb = lib.pcfm_avg_voxelize_forward_workspace(b, c, n, r)
+            ws = _ws(nb, dev)
+            check(lib.pcfm_avg_voxelize_forward(_ptr(features), _ptr(coords), b, c, n, r, _ptr(out), _ptr(ind),
+                                                _ptr(cnt), _ptr(ws), ws.numel(), _stream(features)),
+                  "avg_voxelize_forward")
+        return [out, ind, cnt]
+
+    @staticmethod
+    def avg_voxelize_backward(grad_y, indices, cnt):
+        _chk(grad_y, "grad_y", "f")
+        _chk(indices, "indices", "i")
+        _chk(cnt, "cnt", "i")
+        b, c, s = grad_y.shape
+        n = indices.shape[1]
+        dev = grad_y.device
+        grad_x = torch.empty((b, c, n), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_avg_voxelize_backward_workspace(b, c, n, s), dev)
+            check(lib.pcfm_avg_voxelize_backward(_ptr(grad_y), _ptr(indices), _ptr(cnt), b, c, n, s, _ptr(grad_x),
+                                                 _ptr(ws), ws.numel(), _stream(grad_y)), "avg_voxelize_backward")
+        return grad_x
+
+    # ---- trilinear devoxelization (trilinear_devox.cpp:18-55, 67-91) ----
+    @staticmethod
+    def trilinear_devoxelize_forward(r, is_training, coords, features):
+        _chk(features, "features", "f")
+        _chk(coords, "coords", "f")
+        b, c = features.shape[0], features.shape[1]
+        n = coords.shape[2]
+        r = int(r)
+        dev = features.device
+        outs = torch.empty((b, c, n), dtype=torch.float32, device=dev)
+        if is_training:
+            inds = torch.empty((b, 8, n), dtype=torch.int32, device=dev)
+            wgts = torch.empty((b, 8, n), dtype=torch.float32, device=dev)
+        else:  # trilinear_devox.cpp:45-49: 1-element dummies
+            inds = torch.zeros((1,), dtype=torch.int32, device=dev)
+            wgts = torch.zeros((1,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pcfm_trilinear_devoxelize_forward(_ptr(coords), _ptr(features), b, c, n, r,
+                                                        1 if is_training else 0, _ptr(outs),
+                                                        _ptr(inds) if is_training else None,
+                                                        _ptr(wgts) if is_training else None, _stream(features)),
+                  "trilinear_devoxelize_forward")
+        return [outs, inds, wgts]
+
+    @staticmethod
+    def trilinear_devoxelize_backward(grad_y, indices, weights, r):
+        _chk(grad_y, "grad_y", "f")
+        _chk(weights, "weights", "f")
+        _chk(indices, "indices", "i")
+        b, c, n = grad_y.shape
+        r = int(r)
+        dev = grad_y.device
+        grad_x = torch.empty((b, c, r * r * r), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_trilinear_devoxelize_backward_workspace(b, c, n, r), dev)
+            check(lib.pcfm_trilinear_devoxelize_backward(_ptr(grad_y), _ptr(indices), _ptr(weights), b, c, n, r,
+                                                         _ptr(grad_x), _ptr(ws), ws.numel(), _stream(grad_y)),
+                  "trilinear_devoxelize_backward")
+        return grad_x
+
+    # ---- ball query (ball_query.cpp:6-30) ----
+    @staticmethod
+    def ball_query(centers_coords, points_coords, radius, num_neighbors):
+        _chk(centers_coords, "centers_coords", "f")
+        _chk(points_coords, "points_coords", "f")
+        b, _, m = centers_coords.shape
+        n = points_coords.shape[2]
+        u = int(num_neighbors)
+        dev = centers_coords.device
+        idx = torch.empty((b, m, u), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pcfm_ball_query(_ptr(centers_coords), _ptr(points_coords), b, n, m, float(radius), u,
+                                      _ptr(idx), _stream(centers_coords)), "ball_query")
+        return idx
+
+    # ---- grouping (grouping.cpp:6-44) ----
+    @staticmethod
+    def grouping_forward(features, indices):
+        _chk(features, "features", "f")
+        _chk(indices, "indices", "i")
+        b, c, n = features.shape
+        m, u = indices.shape[1], indices.shape[2]
+        dev = features.device
+        out = torch.empty((b, c, m, u), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pcfm_grouping_forward(_ptr(features), _ptr(indices), b, c, n, m, u, _ptr(out),
+                                            _stream(features)), "grouping_forward")
+        return out
+
+    @staticmethod
+    def grouping_backward(grad_y, indices, n):
+        _chk(grad_y, "grad_y", "f")
+        _chk(indices, "indices", "i")
+        b, c = grad_y.shape[0], grad_y.shape[1]
+        m, u = indices.shape[1], indices.shape[2]
+        n = int(n)
+        dev = grad_y.device
+        grad_x = torch.empty((b, c, n), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_grouping_backward_workspace(b, c, n, m, u), dev)
+            check(lib.pcfm_grouping_backward(_ptr(grad_y), _ptr(indices), b, c, n, m, u, _ptr(grad_x), _ptr(ws),
+                                             ws.numel(), _stream(grad_y)), "grouping_backward")
+        return grad_x
+
+    # ---- gather / FPS (sampling.cpp:6-58) ----
+    @staticmethod
+    def gather_features_forward(features, indices):
+        _chk(features, "features", "f")
+        _chk(indices, "indices", "i")
+        b, c, n = features.shape
+        m = indices.shape[1]
+        dev = features.device
+        out = torch.empty((b, c, m), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pcfm_gather_features_forward(_ptr(features), _ptr(indices), b, c, n, m, _ptr(out),
+                                                   _stream(features)), "gather_features_forward")
+        return out
+
+    @staticmethod
+    def gather_features_backward(grad_y, indices, n):
+        _chk(grad_y, "grad_y", "f")
+        _chk(indices, "indices", "i")
+        b, c = grad_y.shape[0], grad_y.shape[1]
+        m = indices.shape[1]
+        n = int(n)
+        dev = grad_y.device
+        grad_x = torch.empty((b, c, n), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_gather_features_backward_workspace(b, c, n, m), dev)
+            check(lib.pcfm_gather_features_backward(_ptr(grad_y), _ptr(indices), b, c, n, m, _ptr(grad_x),
+                                                    _ptr(ws), ws.numel(), _stream(grad_y)),
+                  "gather_features_backward")
+        return grad_x
+
+    @staticmethod
+    def furthest_point_sampling(coords, num_samples):
+        _chk(coords, "coords", "f")
+        b, _, n = coords.shape
+        m = int(num_samples)
+        dev = coords.device
+        idx = torch.zeros((b, m), dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_furthest_point_sampling_workspace(b, n, m), dev)
+            check(lib.pcfm_furthest_point_sampling(_ptr(coords), b, n, m, _ptr(idx), _ptr(ws), ws.numel(),
+                                                   _stream(coords)), "furthest_point_sampling")
+        return idx
+
+    # ---- 3-NN interpolation (neighbor_interpolate.cpp:6-65) ----
+    @staticmethod
+    def three_nearest_neighbors_interpolate_forward(points_coords, centers_coords, centers_features):
+        _chk(points_coords, "points_coords", "f")
+        _chk(centers_coords, "centers_coords", "f")
+        _chk(centers_features, "centers_features", "f")
+        b, c, m = centers_features.shape
+        n = points_coords.shape[2]
+        dev = points_coords.device
+        idx = torch.empty((b, 3, n), dtype=torch.int32, device=dev)
+        wgt = torch.empty((b, 3, n), dtype=torch.float32, device=dev)
+        out = torch.empty((b, c, n), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pcfm_three_nn_interpolate_forward(_ptr(points_coords), _ptr(centers_coords),
+                                                        _ptr(centers_features), b, c, n, m, _ptr(out), _ptr(idx),
+                                                        _ptr(wgt), _stream(points_coords)),
+                  "three_nearest_neighbors_interpolate_forward")
+        return [out, idx, wgt]
+
+    @staticmethod
+    def three_nearest_neighbors_interpolate_backward(grad_y, indices, weights, m):
+        _chk(grad_y, "grad_y", "f")
+        _chk(indices, "indices", "i")
+        _chk(weights, "weights", "f")
+        b, c, n = grad_y.shape
+        m = int(m)
+        dev = grad_y.device
+        grad_x = torch.empty((b, c, m), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_three_nn_interpolate_backward_workspace(b, c, n, m), dev)
+            check(lib.pcfm_three_nn_interpolate_backward(_ptr(grad_y), _ptr(indices), _ptr(weights), b, c, n, m,
+                                                         _ptr(grad_x), _ptr(ws), ws.numel(), _stream(grad_y)),
+                  "three_nearest_neighbors_interpolate_backward")
+        return grad_x
+
+
+class _Chamfer3D:
+    """`chamfer_3D` (chamfer_cuda.cpp:30-33): caller-allocated outputs, returns 1 on success / 0 on CUDA error."""
+
+    @staticmethod
+    def forward(xyz1, xyz2, dist1, dist2, idx1, idx2):
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        with torch.cuda.device(xyz1.device):
+            rc = lib.pcfm_chamfer3d_forward(_ptr(xyz1), _ptr(xyz2), b, n, m, _ptr(dist1), _ptr(dist2), _ptr(idx1),
+                                            _ptr(idx2), _stream(xyz1))
+        if rc != 0:
+            print(f"error in nnd updateOutput: pcfm rc={rc}")
+            return 0
+        return 1
+
+    @staticmethod
+    def backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2):
+        b, n, _ = xyz1.shape
+        m = xyz2.shape[1]
+        with torch.cuda.device(xyz1.device):
+            rc = lib.pcfm_chamfer3d_backward(_ptr(xyz1), _ptr(xyz2), _ptr(graddist1), _ptr(graddist2), _ptr(idx1),
+                                             _ptr(idx2), b, n, m, _ptr(gradxyz1), _ptr(gradxyz2), _stream(xyz1))
+        if rc != 0:
+            print(f"error in nnd get grad: pcfm rc={rc}")
+            return 0
+        return 1
+
+
+class _EmdExt:
+    """`emd_ext` / `emd_cuda_dynamic` (emd.cpp:23-27)."""
+
+    @staticmethod
+    def _shapes(xyz1, xyz2):
+        b, n, d1 = xyz1.shape
+        b2, m, d2 = xyz2.shape
+        if b2 != b or d1 != 3 or d2 != 3:  # CHECK_EQ in emd_kernel.cu:176-178
+            raise RuntimeError(f"emd: expected xyz1 [B,N,3] and xyz2 [B,M,3], got {tuple(xyz1.shape)} {tuple(xyz2.shape)}")
+        if xyz1.dtype != torch.float32 or xyz2.dtype != torch.float32:
+            raise RuntimeError("emd: only float32 is supported (the reference's Python wrappers cast to float32)")
+        if not (xyz1.is_cuda and xyz2.is_cuda and xyz1.is_contiguous() and xyz2.is_contiguous()):
+            raise RuntimeError("emd: inputs must be contiguous CUDA tensors")
+        return b, n, m
+
+    @staticmethod
+    def approxmatch_forward(xyz1, xyz2):
+        b, n, m = _EmdExt._shapes(xyz1, xyz2)
+        dev = xyz1.device
+        match = torch.empty((b, m, n), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_emd_approxmatch_workspace(b, n, m), dev)
+            check(lib.pcfm_emd_approxmatch_forward(_ptr(xyz1), _ptr(xyz2), b, n, m, _ptr(match), _ptr(ws),
+                                                   ws.numel(), _stream(xyz1)), "approxmatch_forward")
+        return match
+
+    @staticmethod
+    def matchcost_forward(xyz1, xyz2, match):
+        b, n, m = _EmdExt._shapes(xyz1, xyz2)
+        dev = xyz1.device
+        cost = torch.empty((b,), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_emd_matchcost_workspace(b, n, m), dev)
+            check(lib.pcfm_emd_matchcost_forward(_ptr(xyz1), _ptr(xyz2), _ptr(match.contiguous()), b, n, m,
+                                                 _ptr(cost), _ptr(ws), ws.numel(), _stream(xyz1)),
+                  "matchcost_forward")
+        return cost
+
+    @staticmethod
+    def matchcost_backward(grad_cost, xyz1, xyz2, match):
+        b, n, m = _EmdExt._shapes(xyz1, xyz2)
+        dev = xyz1.device
+        grad1 = torch.empty((b, n, 3), dtype=torch.float32, device=dev)
+        grad2 = torch.empty((b, m, 3), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            check(lib.pcfm_emd_matchcost_backward(_ptr(grad_cost.contiguous()), _ptr(xyz1), _ptr(xyz2),
+                                                  _ptr(match.contiguous()), b, n, m, _ptr(grad1), _ptr(grad2),
+                                                  _stream(xyz1)), "matchcost_backward")
+        return [grad1, grad2]
+
+
+pvcnn = _PvcnnBackend()
+chamfer = _Chamfer3D()
+emd = _EmdExt()
+
+
+# ---- new capability: all-pairs blocks for the evaluation harness ----
+def chamfer3d_allpairs(s, r):
+    """cd[i,j] = dist1(S_i,R_j).mean() + dist2(S_i,R_j).mean();  s [ns,N,3], r [nr,M,3] -> [ns,nr]."""
+    if not (s.is_cuda and r.is_cuda and s.dtype == torch.float32 and r.dtype == torch.float32):
+        raise RuntimeError("chamfer3d_allpairs: float32 CUDA tensors required")
+    s, r = s.contiguous(), r.contiguous()
+    ns, n, _ = s.shape
+    nr, m, _ = r.shape
+    out = torch.empty((ns, nr), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        check(lib.pcfm_chamfer3d_allpairs(_ptr(s), _ptr(r), ns, nr, n, m, _ptr(out), _stream(s)),
+              "chamfer3d_allpairs")
+    return out
+
+
+def emd_allpairs(s, r):
+    """emd[i,j] = earth_mover_distance(S_i, R_j, transpose=False) (emd.py:27-51) without materialising match."""
+    if not (s.is_cuda and r.is_cuda and s.dtype == torch.float32 and r.dtype == torch.float32):
+        raise RuntimeError("emd_allpairs: float32 CUDA tensors required")
+    s, r = s.contiguous(), r.contiguous()
+    ns, n, _ = s.shape
+    nr, m, _ = r.shape
+    out = torch.empty((ns, nr), dtype=torch.float32, device=s.device)
+    with torch.cuda.device(s.device):
+        ws = _ws(lib.pcfm_emd_allpairs_workspace(ns, nr, n, m), s.device)
+        check(lib.pcfm_emd_allpairs(_ptr(s), _ptr(r), ns, nr, n, m, _ptr(out), _ptr(ws), ws.numel(), _stream(s)),
+              "emd_allpairs")
+    return out
+
+
+__all__ = ["pvcnn", "chamfer", "emd", "chamfer3d_allpairs", "emd_allpairs", "_lib"]
