@@ -332,6 +332,10 @@ API void oracle_chamfer_backward(const float* xyz1, const float* xyz2, const flo
 }
 
 /* ---- EMD: emd_kernel.cu:24-156 (approxmatch), :199-241 (matchcost), :285-353 (gradients) -------------- */
+/* --use_fast_math (PyTorchEMD/backend.py:20): __expf(x) = ex2.approx.ftz(x * log2(e)) with the product rounded to
+ * fp32 first.  That rounding is the dominant deviation from libm expf for large |x|, so it is restated; the
+ * <= 2 ulp error of the MUFU unit itself cannot be. */
+static inline float fast_expf(float x) { return exp2f(x * 1.4426950408889634f); }
 static inline float d2f(const float* a, const float* c) {
   const float dx = c[0] - a[0], dy = c[1] - a[1], dz = c[2] - a[2];
   return dx * dx + dy * dy + dz * dz;
@@ -356,12 +360,12 @@ API void oracle_emd_approxmatch(const float* xyz1, const float* xyz2, int b, int
       if (j == -2) level = 0;
       for (int k = 0; k < n; ++k) {
         float suml = 1e-9f;
-        for (int l = 0; l < m; ++l) suml += expf(level * d2f(p1 + k * 3, p2 + l * 3)) * remainR[l];
+        for (int l = 0; l < m; ++l) suml += fast_expf(level * d2f(p1 + k * 3, p2 + l * 3)) * remainR[l];
         ratioL[k] = remainL[k] / suml;
       }
       for (int l = 0; l < m; ++l) {
         float sumr = 0;
-        for (int k = 0; k < n; ++k) sumr += expf(level * d2f(p1 + k * 3, p2 + l * 3)) * ratioL[k];
+        for (int k = 0; k < n; ++k) sumr += fast_expf(level * d2f(p1 + k * 3, p2 + l * 3)) * ratioL[k];
         sumr *= remainR[l];
         const float consumption = fminf(remainR[l] / (sumr + 1e-9f), 1.0f);
         ratioR[l] = consumption * remainR[l];
@@ -371,7 +375,7 @@ API void oracle_emd_approxmatch(const float* xyz1, const float* xyz2, int b, int
         float suml = 0;
         const float rl = ratioL[k];
         for (int l = 0; l < m; ++l) {
-          const float w = expf(level * d2f(p1 + k * 3, p2 + l * 3)) * rl * ratioR[l];
+          const float w = fast_expf(level * d2f(p1 + k * 3, p2 + l * 3)) * rl * ratioR[l];
           mt[(size_t)l * n + k] += w;
           suml += w;
         }

@@ -1,0 +1,428 @@
+"""GPU parity tests: the sm_100a kernels, called through the C ABI (pcfm.backend is a ctypes shim over
+include/pcfm_b200.h), against the CPU oracle on the same seeded inputs, and — when oracle/_ref was built —
+against the UNMODIFIED reference CUDA kernels running on the same GPU.
+
+Bars (north_star): integer outputs (voxel / neighbour / arg-min indices, counts) bit-exact;
+fp32 values within 1e-5 (tests/util.py states the exact rule)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import cases  # noqa: E402
+from util import assert_close, assert_equal, rng  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+def cu(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def host(x):
+    return x.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def be():
+    from pcfm import backend
+    return backend
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import cpu_ref
+    cpu_ref.build()
+    return cpu_ref
+
+
+@pytest.fixture(scope="module")
+def ref():
+    """The compiled reference extensions (None if oracle/_ref is absent)."""
+    from oracle import build_ref
+    out = {}
+    for k in ("pvcnn", "chamfer", "emd"):
+        try:
+            out[k] = build_ref.load_ref(k)
+        except Exception as e:  # noqa: BLE001
+            print(f"oracle/_ref {k} not loadable: {e}")
+            out[k] = None
+    return out
+
+
+def gpu_voxel_coords(coords, res):
+    """modules/voxelization.py:16-24 on the GPU (what both the reference module and pcfm.nn.Voxelization run)."""
+    c = cu(coords)
+    nc = c - c.mean(2, keepdim=True)
+    nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 0) + 0.5
+    nc = torch.clamp(nc * res, 0, res - 1)
+    return torch.round(nc).to(torch.int32).contiguous(), nc
+
+
+# ------------------------------------------------------------------------------------------------ voxelize
+VOX_SHAPES = [
+    dict(seed=1, b=2, c=64, n=2048, res=32),                    # BASELINE config 1
+    dict(seed=2, b=2, c=3, n=1001, res=7),                      # odd sizes: no 16-byte alignment anywhere
+    dict(seed=3, b=1, c=4, n=4096, res=4, kind="clustered"),    # hundreds of points per voxel
+    dict(seed=4, b=1, c=1, n=1, res=2),
+    dict(seed=5, b=3, c=16, n=20000, res=32),                   # config-2 point count
+    dict(seed=6, b=2, c=32, n=20000, res=8),                    # long segments (config-2 stage 3)
+]
+
+
+@pytest.mark.parametrize("kw", VOX_SHAPES, ids=lambda k: f"b{k['b']}c{k['c']}n{k['n']}r{k['res']}")
+@pytest.mark.parametrize("variant", [0, 1], ids=["csr", "atomic"])
+def test_avg_voxelize(be, oracle, ref, kw, variant):
+    from pcfm import _lib
+    feat, coords, res = cases.voxel_case(**kw)
+    vox, _ = gpu_voxel_coords(coords, res)
+    _lib.set_option("vox_fwd", variant)
+    try:
+        out, ind, cnt = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res)
+    finally:
+        _lib.set_option("vox_fwd", 0)
+    o_out, o_ind, o_cnt = oracle.avg_voxelize_forward(feat, host(vox), res)
+    assert_equal(host(ind), o_ind, "ind")
+    assert_equal(host(cnt), o_cnt, "cnt")
+    if variant == 0:
+        assert_equal(host(out), o_out, "out (ascending-order sum is bit-identical to the oracle)")
+    else:
+        assert_close(host(out), o_out, "out")
+    gy = rng(kw["seed"] + 100).standard_normal(o_out.shape).astype(np.float32)
+    gx = be.pvcnn.avg_voxelize_backward(cu(gy), ind, cnt)
+    assert_equal(host(gx), oracle.avg_voxelize_backward(gy, o_ind, o_cnt), "grad_x")
+    if ref["pvcnn"] is not None and variant == 0:
+        r_out, r_ind, r_cnt = ref["pvcnn"].avg_voxelize_forward(cu(feat), vox, res)
+        assert_equal(host(ind), host(r_ind), "ind vs reference")
+        assert_equal(host(cnt), host(r_cnt), "cnt vs reference")
+        assert_close(host(out), host(r_out), "out vs reference")
+        assert_close(host(gx), host(ref["pvcnn"].avg_voxelize_backward(cu(gy), r_ind, r_cnt)), "grad vs reference")
+
+
+def test_avg_voxelize_stage_variants_agree(be):
+    from pcfm import _lib
+    feat, coords, res = cases.voxel_case(seed=9, b=2, c=8, n=4000, res=16)
+    vox, _ = gpu_voxel_coords(coords, res)
+    a = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res)[0]
+    _lib.set_option("stage", 1)
+    try:
+        b = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res)[0]
+    finally:
+        _lib.set_option("stage", 0)
+    assert_equal(host(a), host(b), "TMA-bulk vs plain staging")
+
+
+# ------------------------------------------------------------------------------------------------ devoxelize
+DEVOX_SHAPES = [
+    dict(seed=11, b=2, c=64, n=2048, res=32),
+    dict(seed=12, b=1, c=3, n=333, res=5),
+    dict(seed=13, b=2, c=16, n=20000, res=16),
+    dict(seed=14, b=2, c=16, n=20000, res=8),
+    dict(seed=15, b=1, c=5, n=7, res=2),
+]
+
+
+@pytest.mark.parametrize("kw", DEVOX_SHAPES, ids=lambda k: f"b{k['b']}c{k['c']}n{k['n']}r{k['res']}")
+def test_trilinear_devoxelize(be, oracle, ref, kw):
+    from pcfm import _lib
+    coords, vox, gy, res = cases.devox_case(**kw)
+    outs, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(coords), cu(vox))
+    o_outs, o_inds, o_wgts = oracle.trilinear_devoxelize_forward(res, coords, vox)
+    assert_equal(host(inds), o_inds, "inds")
+    assert_equal(host(wgts), o_wgts, "wgts (products of exact factors: bit-exact)")
+    assert_close(host(outs), o_outs, "outs")
+    e_outs, e_inds, e_wgts = be.pvcnn.trilinear_devoxelize_forward(res, False, cu(coords), cu(vox))
+    assert tuple(e_inds.shape) == (1,) and tuple(e_wgts.shape) == (1,)     # trilinear_devox.cpp:45-49
+    assert_equal(host(e_outs), host(outs), "eval-mode outs")
+    o_gx = oracle.trilinear_devoxelize_backward(gy, o_inds, o_wgts, res)
+    for variant in (0, 1):
+        _lib.set_option("devox_bwd", variant)
+        try:
+            gx = be.pvcnn.trilinear_devoxelize_backward(cu(gy), inds, wgts, res)
+        finally:
+            _lib.set_option("devox_bwd", 0)
+        assert_close(host(gx), o_gx, f"grad_x variant {variant}")
+    if ref["pvcnn"] is not None:
+        r_outs, r_inds, r_wgts = ref["pvcnn"].trilinear_devoxelize_forward(res, True, cu(coords), cu(vox))
+        assert_equal(host(inds), host(r_inds), "inds vs reference")
+        assert_equal(host(wgts), host(r_wgts), "wgts vs reference")
+        assert_close(host(outs), host(r_outs), "outs vs reference")
+        assert_close(host(be.pvcnn.trilinear_devoxelize_backward(cu(gy), inds, wgts, res)),
+                     host(ref["pvcnn"].trilinear_devoxelize_backward(cu(gy), r_inds, r_wgts, res)), "grad vs reference")
+
+
+def test_devox_backward_is_deterministic(be):
+    """Sorted segmented sums: run-to-run bit-identical (segments up to 2048 edges are put in ascending edge order;
+    csr.cu kMaxSortedSeg).  devox_case piles n/8 points on each of two corners, so keep 8*n/8 under that cap."""
+    coords, vox, gy, res = cases.devox_case(seed=16, b=2, c=8, n=2000, res=16)
+    _, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(coords), cu(vox))
+    a = host(be.pvcnn.trilinear_devoxelize_backward(cu(gy), inds, wgts, res))
+    for _ in range(3):
+        assert_equal(host(be.pvcnn.trilinear_devoxelize_backward(cu(gy), inds, wgts, res)), a, "run-to-run")
+
+
+# ------------------------------------------------------------------------------------------------ pointnet ops
+PN_SHAPES = [
+    dict(seed=41, b=2, c=5, n=1024, m=256, kind="rand"),
+    dict(seed=42, b=2, c=3, n=600, m=150, kind="lattice"),      # exact ties everywhere
+    dict(seed=43, b=1, c=2, n=20, m=7, kind="rand"),             # fewer points than a warp
+    dict(seed=44, b=2, c=4, n=5000, m=1250, kind="rand"),
+]
+
+
+@pytest.mark.parametrize("kw", PN_SHAPES, ids=lambda k: f"{k['kind']}n{k['n']}m{k['m']}")
+def test_fps_ballquery_grouping_gather_3nn(be, oracle, ref, kw):
+    pts, feat, cfeat = cases.pointnet_case(**kw)
+    n, m = kw["n"], kw["m"]
+    fidx = be.pvcnn.furthest_point_sampling(cu(pts), m)
+    o_fidx = oracle.furthest_point_sampling(pts, m)
+    assert_equal(host(fidx), o_fidx, "fps indices (reference tie-break)")
+    centers = be.pvcnn.gather_features_forward(cu(pts), fidx)
+    o_centers = oracle.gather_forward(pts, o_fidx)
+    assert_equal(host(centers), o_centers, "gather")
+    for radius, u in [(cases.BALL["radius"], cases.BALL["u"]), (0.05, 3), (10.0, 40)]:
+        bq = be.pvcnn.ball_query(centers, cu(pts), radius, u)
+        o_bq = oracle.ball_query(o_centers, pts, radius, u)
+        assert_equal(host(bq), o_bq, f"ball_query r={radius} u={u}")
+    bq = be.pvcnn.ball_query(centers, cu(pts), cases.BALL["radius"], cases.BALL["u"])
+    grp = be.pvcnn.grouping_forward(cu(feat), bq)
+    assert_equal(host(grp), oracle.grouping_forward(feat, o_bq if False else host(bq)), "grouping")
+    ggy = rng(kw["seed"] + 7).standard_normal(tuple(grp.shape)).astype(np.float32)
+    ggx = be.pvcnn.grouping_backward(cu(ggy), bq, n)
+    assert_close(host(ggx), oracle.grouping_backward(ggy, host(bq), n), "grouping backward")
+    gg = be.pvcnn.gather_features_backward(cu(cfeat), fidx, n)
+    assert_close(host(gg), oracle.gather_backward(cfeat, o_fidx, n), "gather backward")
+    o3, i3, w3 = be.pvcnn.three_nearest_neighbors_interpolate_forward(cu(pts), centers, cu(cfeat))
+    oo3, oi3, ow3 = oracle.three_nn_interpolate_forward(pts, o_centers, cfeat)
+    assert_equal(host(i3), oi3, "3nn indices")
+    assert_equal(host(w3), ow3, "3nn weights")
+    assert_close(host(o3), oo3, "3nn interpolate")
+    g3 = be.pvcnn.three_nearest_neighbors_interpolate_backward(cu(feat), i3, w3, m)
+    assert_close(host(g3), oracle.three_nn_interpolate_backward(feat, oi3, ow3, m), "3nn backward")
+    if ref["pvcnn"] is not None:
+        R = ref["pvcnn"]
+        assert_equal(host(fidx), host(R.furthest_point_sampling(cu(pts), m)), "fps vs reference")
+        assert_equal(host(bq), host(R.ball_query(centers, cu(pts), cases.BALL["radius"], cases.BALL["u"])), "ball vs reference")
+        assert_equal(host(grp), host(R.grouping_forward(cu(feat), bq)), "grouping vs reference")
+        assert_close(host(ggx), host(R.grouping_backward(cu(ggy), bq, n)), "grouping bwd vs reference")
+        r3, ri3, rw3 = R.three_nearest_neighbors_interpolate_forward(cu(pts), centers, cu(cfeat))
+        assert_equal(host(i3), host(ri3), "3nn idx vs reference")
+        assert_equal(host(w3), host(rw3), "3nn w vs reference")
+        assert_close(host(o3), host(r3), "3nn out vs reference")
+        assert_close(host(g3), host(R.three_nearest_neighbors_interpolate_backward(cu(feat), ri3, rw3, m)), "3nn bwd vs reference")
+
+
+def test_ball_query_no_hit_rows_are_zero(be):
+    pts = np.zeros((1, 3, 64), np.float32)
+    ctr = np.full((1, 3, 5), 100.0, np.float32)
+    assert host(be.pvcnn.ball_query(cu(ctr), cu(pts), 0.5, 8)).sum() == 0
+
+
+# ------------------------------------------------------------------------------------------------ chamfer
+CH_SHAPES = [
+    dict(seed=21, b=4, n=100, m=200, kind="rand"),          # unit_test.py:15-16
+    dict(seed=22, b=2, n=700, m=513, kind="lattice"),
+    dict(seed=23, b=1, n=2500, m=2300, kind="randn"),       # crosses the 2048-point chunk
+    dict(seed=24, b=2, n=2048, m=2048, kind="randn"),       # README check shape
+    dict(seed=25, b=1, n=3, m=1, kind="randn"),
+    dict(seed=26, b=32, n=2000, m=1000, kind="rand"),       # the reference's published timing shape
+]
+
+
+def run_chamfer(mod, a, c):
+    b, n, m = a.shape[0], a.shape[1], c.shape[1]
+    d1 = torch.zeros(b, n, device="cuda"); d2 = torch.zeros(b, m, device="cuda")
+    i1 = torch.zeros(b, n, dtype=torch.int32, device="cuda"); i2 = torch.zeros(b, m, dtype=torch.int32, device="cuda")
+    assert mod.forward(cu(a), cu(c), d1, d2, i1, i2) == 1
+    return d1, d2, i1, i2
+
+
+@pytest.mark.parametrize("kw", CH_SHAPES, ids=lambda k: f"{k['kind']}b{k['b']}n{k['n']}m{k['m']}")
+def test_chamfer(be, oracle, ref, kw):
+    a, c = cases.cloud_pair(**kw)
+    d1, d2, i1, i2 = run_chamfer(be.chamfer, a, c)
+    od1, od2, oi1, oi2 = oracle.chamfer_forward(a, c)
+    assert_equal(host(i1), oi1, "idx1"); assert_equal(host(i2), oi2, "idx2")
+    assert_equal(host(d1), od1, "dist1"); assert_equal(host(d2), od2, "dist2")
+    b, n, m = a.shape[0], a.shape[1], c.shape[1]
+    gd1 = rng(kw["seed"] + 1).standard_normal((b, n)).astype(np.float32)
+    gd2 = rng(kw["seed"] + 2).standard_normal((b, m)).astype(np.float32)
+    g1 = torch.zeros(b, n, 3, device="cuda"); g2 = torch.zeros(b, m, 3, device="cuda")
+    assert be.chamfer.backward(cu(a), cu(c), g1, g2, cu(gd1), cu(gd2), i1, i2) == 1
+    og1, og2 = oracle.chamfer_backward(a, c, gd1, gd2, oi1, oi2)
+    assert_close(host(g1), og1, "gradxyz1"); assert_close(host(g2), og2, "gradxyz2")
+    if ref["chamfer"] is not None:
+        rd1, rd2, ri1, ri2 = run_chamfer(ref["chamfer"], a, c)
+        assert_equal(host(i1), host(ri1), "idx1 vs reference"); assert_equal(host(i2), host(ri2), "idx2 vs reference")
+        assert_equal(host(d1), host(rd1), "dist1 vs reference"); assert_equal(host(d2), host(rd2), "dist2 vs reference")
+
+
+def test_chamfer_same_cloud_is_zero(be):
+    """README.md:116-134: CD(x, x) == 0 with idx[i] == i."""
+    x = rng(0).standard_normal((2, 2048, 3)).astype(np.float32)
+    d1, d2, i1, i2 = run_chamfer(be.chamfer, x, x)
+    assert float(d1.mean() + d2.mean()) == 0.0
+    assert_equal(host(i1), np.tile(np.arange(2048, dtype=np.int32), (2, 1)), "idx")
+
+
+def test_chamfer_matches_float64_reference_method(be):
+    """unit_test.py:14-35: MSE vs the float64 pairwise method < 1e-8 and identical indices."""
+    p1 = torch.rand(4, 100, 3, generator=torch.Generator().manual_seed(3))
+    p2 = torch.rand(4, 200, 3, generator=torch.Generator().manual_seed(4))
+    d1, d2, i1, i2 = run_chamfer(be.chamfer, p1.numpy(), p2.numpy())
+    x, y = p1.double(), p2.double()
+    P = (x.pow(2).sum(2)[:, :, None] + y.pow(2).sum(2)[:, None, :] - 2 * torch.bmm(x, y.transpose(2, 1)))
+    md1, mi1 = P.min(2); md2, mi2 = P.min(1)
+    assert float(((d1.cpu() - md1.float()) ** 2).mean() + ((d2.cpu() - md2.float()) ** 2).mean()) < 1e-8
+    assert torch.equal(i1.cpu().long(), mi1) and torch.equal(i2.cpu().long(), mi2)
+
+
+def test_chamfer_autograd_wrapper(be, oracle):
+    from pcfm.metrics import chamfer_3DDist
+    a, c = cases.cloud_pair(seed=27, b=2, n=300, m=200)
+    x1 = cu(a).requires_grad_(True); x2 = cu(c).requires_grad_(True)
+    d1, d2, i1, i2 = chamfer_3DDist()(x1, x2)
+    (d1.sum() + 0.5 * d2.sum()).backward()
+    od1, od2, oi1, oi2 = oracle.chamfer_forward(a, c)
+    og1, og2 = oracle.chamfer_backward(a, c, np.ones_like(od1), 0.5 * np.ones_like(od2), oi1, oi2)
+    assert_close(host(x1.grad), og1, "grad1"); assert_close(host(x2.grad), og2, "grad2")
+
+
+# ------------------------------------------------------------------------------------------------ EMD
+EMD_SHAPES = [
+    dict(seed=31, b=2, n=256, m=256, kind="rand"),
+    dict(seed=32, b=2, n=300, m=150, kind="rand"),     # n = 2m: multiR = 2
+    dict(seed=33, b=1, n=100, m=250, kind="rand"),     # multiL = 2 (integer division)
+    dict(seed=34, b=2, n=1024, m=1024, kind="rand"),   # README check shape
+]
+
+
+@pytest.mark.parametrize("kw", EMD_SHAPES, ids=lambda k: f"b{k['b']}n{k['n']}m{k['m']}")
+def test_emd(be, oracle, ref, kw):
+    a, c = cases.cloud_pair(**kw)
+    match = be.emd.approxmatch_forward(cu(a), cu(c))
+    cost = be.emd.matchcost_forward(cu(a), cu(c), match)
+    o_match = oracle.emd_approxmatch(a, c)
+    o_cost = oracle.emd_matchcost(a, c, o_match)
+    assert_close(host(cost), o_cost, "cost", rtol=1e-5)
+    assert_close(host(match).sum(2), o_match.sum(2), "match row sums", rtol=2e-5)
+    assert_close(host(match).sum(1), o_match.sum(1), "match col sums", rtol=2e-5)
+    gc = np.linspace(0.5, 1.5, a.shape[0]).astype(np.float32)
+    g1, g2 = be.emd.matchcost_backward(cu(gc), cu(a), cu(c), match)
+    og1, og2 = oracle.emd_matchcost_backward(gc, a, c, host(match))
+    assert_close(host(g1), og1, "grad1"); assert_close(host(g2), og2, "grad2")
+    if ref["emd"] is not None:
+        r_match = ref["emd"].approxmatch_forward(cu(a), cu(c))
+        r_cost = ref["emd"].matchcost_forward(cu(a), cu(c), r_match)
+        assert_close(host(cost), host(r_cost), "cost vs reference")
+        assert_close(host(match), host(r_match), "match vs reference", rtol=2e-5, atol_frac=2e-6)
+        rg1, rg2 = ref["emd"].matchcost_backward(cu(gc), cu(a), cu(c), r_match)
+        assert_close(host(g1), host(rg1), "grad1 vs reference"); assert_close(host(g2), host(rg2), "grad2 vs reference")
+
+
+def test_emd_known_answer(be):
+    """test_emd_loss.py:7-43: d = 0.355 per batch element, loss = d0/2 + 2 d1 + d2/3 = 2.011667/2, analytic grads."""
+    from pcfm.metrics import earth_mover_distance
+    p1 = torch.tensor([[[1.7, -0.1, 0.1], [0.1, 1.2, 0.3]]]).repeat(3, 1, 1).cuda().requires_grad_(True)
+    p2 = torch.tensor([[[0.3, 1.8, 0.2], [1.2, -0.2, 0.3]]]).repeat(3, 1, 1).cuda().requires_grad_(True)
+    d = earth_mover_distance(p1, p2, transpose=False)
+    assert torch.allclose(d.cpu(), torch.full((3,), 0.355), atol=1e-5)
+    loss = d[0] / 2 + d[1] * 2 + d[2] / 3
+    assert abs(float(loss) - 2.011667 / 2) < 1e-4   # gt_dist (2.011667) is the cost before the division by N=2
+    loss.backward()
+    q1 = p1.detach().clone().requires_grad_(True); q2 = p2.detach().clone().requires_grad_(True)
+    gt = ((((q1[0, 0] - q2[0, 1]) ** 2).sum() + ((q1[0, 1] - q2[0, 0]) ** 2).sum()) / 2
+          + (((q1[1, 0] - q2[1, 1]) ** 2).sum() + ((q1[1, 1] - q2[1, 0]) ** 2).sum()) * 2
+          + (((q1[2, 0] - q2[2, 1]) ** 2).sum() + ((q1[2, 1] - q2[2, 0]) ** 2).sum()) / 3) / 2
+    gt.backward()
+    assert torch.allclose(p1.grad, q1.grad, atol=1e-4) and torch.allclose(p2.grad, q2.grad, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------------------------ all-pairs
+def test_allpairs_chamfer_equals_operator(be, oracle):
+    r = rng(51)
+    s = (r.standard_normal((5, 700, 3)) * 0.3).astype(np.float32)
+    q = (r.standard_normal((4, 900, 3)) * 0.3).astype(np.float32)
+    s[1, :50] = s[1, 50:100]   # duplicated points
+    cd = host(be.chamfer3d_allpairs(cu(s), cu(q)))
+    for i in range(5):
+        for j in range(4):
+            d1, d2, _, _ = oracle.chamfer_forward(s[i:i + 1], q[j:j + 1])
+            want = d1.astype(np.float64).mean() + d2.astype(np.float64).mean()
+            assert abs(cd[i, j] - want) <= 1e-5 * abs(want), (i, j, cd[i, j], want)
+
+
+def test_allpairs_chamfer_full_size_properties(be):
+    """BASELINE config 4 point count (2048): symmetry cd(S,R) == cd(R,S)^T bit-exact, zero diagonal on cd(S,S)."""
+    r = rng(52)
+    s = (r.standard_normal((6, 2048, 3)) * 0.3).astype(np.float32)
+    q = (r.standard_normal((7, 2048, 3)) * 0.3).astype(np.float32)
+    a = host(be.chamfer3d_allpairs(cu(s), cu(q)))
+    b = host(be.chamfer3d_allpairs(cu(q), cu(s)))
+    assert_close(a, b.T, "cd(S,R) vs cd(R,S)^T", rtol=1e-6)
+    assert np.all(np.diag(host(be.chamfer3d_allpairs(cu(s), cu(s)))) == 0.0)
+
+
+def test_allpairs_emd_equals_operator(be, oracle):
+    r = rng(53)
+    s = r.random((3, 256, 3)).astype(np.float32)
+    q = r.random((2, 256, 3)).astype(np.float32)
+    got = host(be.emd_allpairs(cu(s), cu(q)))
+    from pcfm.metrics import earth_mover_distance_nograd
+    for i in range(3):
+        for j in range(2):
+            want_op = float(earth_mover_distance_nograd(cu(s[i:i + 1]), cu(q[j:j + 1]), transpose=False))
+            want_or = float(oracle.earth_mover_distance(s[i:i + 1], q[j:j + 1])[0])
+            assert abs(got[i, j] - want_op) <= 1e-5 * abs(want_op), (i, j, got[i, j], want_op)
+            assert abs(got[i, j] - want_or) <= 2e-5 * abs(want_or), (i, j, got[i, j], want_or)
+
+
+def test_metrics_harness_single_gpu(be):
+    from pcfm import evaluation as ev
+    r = rng(54)
+    s = cu((r.standard_normal((12, 512, 3)) * 0.3).astype(np.float32))
+    q = cu((r.standard_normal((10, 512, 3)) * 0.3).astype(np.float32))
+    res = ev.compute_metrics(s, q, metrics=("cd", "emd"), block=5)
+    for k in ("cd", "emd"):
+        assert res[k]["mmd"] > 0 and 0 < res[k]["cov"] <= 1 and 0 <= res[k]["1nna"] <= 1
+    full = ev.pairwise_matrix(s, q, "cd", block=100)
+    blocked = ev.pairwise_matrix(s, q, "cd", block=5)
+    assert torch.equal(full, blocked)
+
+
+# ------------------------------------------------------------------------------------------------ modules
+def test_pvconv_module_forward_backward_and_eval_contract(be, oracle):
+    from pcfm.nn import PVConv
+    torch.manual_seed(0)
+    m = PVConv(16, 16, 3, 8, with_se=True, normalize=True, eps=1e-6).cuda()
+    f = torch.randn(2, 16, 500, device="cuda", requires_grad=True)
+    c = torch.randn(2, 3, 500, device="cuda")
+    out, c2 = m((f, c))
+    assert out.shape == (2, 16, 500) and c2 is c
+    out.square().mean().backward()
+    assert f.grad is not None and torch.isfinite(f.grad).all()
+    # the voxel branch alone against the oracle
+    vox, nc = m.voxelization(f.detach(), c)
+    o_vox, o_nc, _, _, _ = oracle.voxelization_module(host(f), host(c), 8, True, 1e-6)
+    assert_close(host(vox).reshape(2, 16, -1), o_vox, "Voxelization module")
+    m.eval()
+    f2 = f.detach().clone().requires_grad_(True)
+    out2, _ = m((f2, c))
+    with pytest.raises(Exception):   # nothing saved in eval mode (devoxelization.py:24-26)
+        out2.sum().backward()
+
+
+def test_inputs_are_not_mutated_and_streams_are_respected(be):
+    feat, coords, res = cases.voxel_case(seed=61, b=2, c=8, n=3000, res=16)
+    vox, _ = gpu_voxel_coords(coords, res)
+    f = cu(feat); f0 = f.clone(); v0 = vox.clone()
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        out, ind, cnt = be.pvcnn.avg_voxelize_forward(f, vox, res)
+    s.synchronize()
+    ref_out = be.pvcnn.avg_voxelize_forward(f, vox, res)[0]
+    torch.cuda.synchronize()
+    assert torch.equal(out, ref_out) and torch.equal(f, f0) and torch.equal(vox, v0)
