@@ -1,0 +1,375 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the point-cloud hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (config 2 of BASELINE.json, named in `config.workload`): the PVConv point-voxel primitive chain of one
+HybridMLP velocity-net step — B=8 clouds of N=20000 points through the 6 PVConv instances of ContextNet
+(models.py:402-404: 2x(C=128,r=32), 2x(C=256,r=16), 2x(C=256,r=8)); per instance avg_voxelize forward,
+trilinear_devoxelize forward (training mode), trilinear_devoxelize backward, avg_voxelize backward.
+One step = all 6 chains, forward + backward.  value = 6*B*N point-passes / step time, in Mpts/s.
+Conv3d / BatchNorm between the primitives are cuDNN library calls outside the path and are not
+timed; each primitive reads tensors that no kernel of the same step has just written (nothing is L2-hot).
+
+Also measured and reported in the same JSON line:
+  roofline      dominant primitive: algorithmic bytes (SURVEY.md 8d formulas) / its CUDA-event time vs measured HBM peak
+  e2e           the same chains through the autograd operator API with HOST (pinned) inputs and outputs
+  cpu_baseline  the same ops in stock PyTorch on the host cores (oracle/torch_cpu.py), bounded sample
+  allpairs      all-pairs Chamfer / EMD cloud-pairs/s (config 4 shapes), rows sharded over the N ranks
+
+--impl reference runs only the PyTorch-CPU arm (rank 0) and prints the same line shape.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "point-cloud-flow-matching_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "pvconv_primitives_fwd_bwd_mpts_per_s"
+UNIT = "Mpts/s"
+B, NPTS = 8, 20000
+STAGES = [(128, 32), (128, 32), (256, 16), (256, 16), (256, 8), (256, 8)]  # (C, r) of the 6 PVConv instances
+CONFIG = {
+    "workload": "BASELINE.json configs[1]: PVConv primitive chain of one velocity-net step, B=8, N=20000, "
+                "(C,r) = 2x(128,32) 2x(256,16) 2x(256,8); vox fwd + devox fwd(train) + devox bwd + vox bwd per instance",
+    "batch": B, "points": NPTS, "stages": STAGES,
+    "l2": "inputs larger than L2: ~4.8 GB touched per step, every primitive reads tensors not written in that step",
+    "parallelism": "one process per GPU, replicas (data parallel), no data-path collective",
+}
+
+
+def algorithmic_bytes(op, c, r, b=B, n=NPTS):
+    s = r ** 3
+    return {  # SURVEY.md 8(d); zero-fill of outputs not counted
+        "vox_fwd": 4 * b * (c * n + 3 * n + c * s + n + s),
+        "vox_bwd": 4 * b * (c * s + n + s + c * n),
+        "devox_fwd": 4 * b * (3 * n + c * s + c * n + 16 * n),
+        "devox_bwd": 4 * b * (c * n + 16 * n + c * s),
+    }[op]
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "200"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        rows = [ln.strip().split(", ") for ln in open(self.f.name) if ln.strip()]
+        os.unlink(self.f.name)
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+def measured_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:  # noqa: BLE001
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------------------
+def cpu_chain_step(torch, tc, feats, coords, batch):
+    """One bounded sample of the workload on the host: one chain per distinct stage shape."""
+    pts = 0
+    for (c, r), f, x in zip([(128, 32), (256, 16), (256, 8)], feats, coords):
+        tc.pvconv_primitives_fwd_bwd(f[:batch], x[:batch], r)
+        pts += batch * NPTS
+    return pts
+
+
+def make_cpu_inputs(torch):
+    g = torch.Generator().manual_seed(0)
+    feats = [torch.randn(B, c, NPTS, generator=g) for c in (128, 256, 256)]
+    coords = [torch.randn(B, 3, NPTS, generator=g) for _ in range(3)]
+    return feats, coords
+
+
+def run_reference_arm(args):
+    """PyTorch-CPU statement of the path on the host cores (the reference ships no CPU implementation of its CUDA
+    kernels; north_star names this arm: scatter_add voxelize, grid_sample devoxelize, autograd backward)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import torch_cpu as tc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    feats, coords = make_cpu_inputs(torch)
+    t0 = time.perf_counter()
+    cpu_chain_step(torch, tc, feats, coords, 2)            # probe at B=2
+    probe = time.perf_counter() - t0
+    budget = 150.0                                          # seconds for the whole K+W run
+    batch = B
+    while batch > 1 and probe * (batch / 2) * (args.steps + args.warmup) > budget:
+        batch //= 2
+    for _ in range(args.warmup):
+        cpu_chain_step(torch, tc, feats, coords, batch)
+    t0 = time.perf_counter()
+    pts = 0
+    for _ in range(args.steps):
+        pts += cpu_chain_step(torch, tc, feats, coords, batch)
+    dt = time.perf_counter() - t0
+    val = pts / dt / 1e6
+    sample = f"per step: one chain per stage shape (3 of the 6), batch {batch} of {B}, N={NPTS}"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    import pcfm  # noqa: F401
+    from pcfm import _lib, backend as be
+    from pcfm import functional as F
+    from pcfm.nn import Voxelization
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- resident inputs: distinct buffers per PVConv instance ----------------
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    chains = []
+    for (c, r) in STAGES:
+        feat = torch.randn(B, c, NPTS, device=dev, generator=g)
+        coords = torch.randn(B, 3, NPTS, device=dev, generator=g)
+        nc = coords - coords.mean(2, keepdim=True)                         # modules/voxelization.py:16-24
+        nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 1e-6) + 0.5
+        nc = torch.clamp(nc * r, 0, r - 1).contiguous()
+        vox = torch.round(nc).to(torch.int32).contiguous()
+        chains.append(dict(c=c, r=r, feat=feat, nc=nc, vox=vox,
+                           conv_out=torch.randn(B, c, r ** 3, device=dev, generator=g),     # what devox fwd reads
+                           gy=torch.randn(B, c, NPTS, device=dev, generator=g),             # upstream grad of devox
+                           gconv=torch.randn(B, c, r ** 3, device=dev, generator=g)))       # what vox bwd reads
+    P = be.pvcnn
+
+    def step(rec=None):
+        for ch in chains:
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if rec is not None else None
+            if ev: ev[0].record()
+            out, ind, cnt = P.avg_voxelize_forward(ch["feat"], ch["vox"], ch["r"])
+            if ev: ev[1].record()
+            outs, inds, wgts = P.trilinear_devoxelize_forward(ch["r"], True, ch["nc"], ch["conv_out"])
+            if ev: ev[2].record()
+            ggrid = P.trilinear_devoxelize_backward(ch["gy"], inds, wgts, ch["r"])
+            if ev: ev[3].record()
+            gfeat = P.avg_voxelize_backward(ch["gconv"], ind, cnt)
+            if ev:
+                ev[4].record()
+                rec.append((ch["c"], ch["r"], ev))
+        return gfeat
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    clocks = sampler.stop() if sampler else None
+    ms_per_step = ms / args.steps
+    pts_per_step = len(STAGES) * B * NPTS * world
+    value = pts_per_step / (ms_per_step * 1e-3) / 1e6
+
+    # ---------------- per-primitive CUDA-event times (same launches, instrumented pass) ----------------
+    rec = []
+    for _ in range(3):
+        step(rec)
+    torch.cuda.synchronize()
+    per = {}
+    for c, r, ev in rec:
+        for k, name in enumerate(["vox_fwd", "devox_fwd", "devox_bwd", "vox_bwd"]):
+            per.setdefault((name, c, r), []).append(ev[k].elapsed_time(ev[k + 1]))
+    peak, peak_src = measured_peak_gbs()
+    prim = []
+    for (name, c, r), ts in sorted(per.items()):
+        t = statistics.mean(ts)
+        by = algorithmic_bytes(name, c, r)
+        prim.append({"op": name, "C": c, "r": r, "ms": round(t, 4), "GBps": round(by / t / 1e6, 1),
+                     "frac": round(by / t / 1e6 / peak, 4)})
+    top = max(prim, key=lambda d: d["ms"])
+    top_bytes = algorithmic_bytes(top["op"], top["C"], top["r"])
+    tot_bytes = sum(algorithmic_bytes(n_, c, r) * len(ts) / 3 for (n_, c, r), ts in per.items())
+    roofline = {"bound": "hbm", "kernel": f"{top['op']} C={top['C']} r={top['r']} (op = plan kernels + row kernel)",
+                "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": round(top["GBps"] / peak, 4),
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": top_bytes,
+                "step_aggregate": {"algorithmic_GB_per_step": round(tot_bytes / 1e9, 3),
+                                   "achieved_GBps": round(tot_bytes / (ms_per_step * 1e-3) / 1e9 * 1.0, 1),
+                                   "frac": round(tot_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4)},
+                "per_primitive": prim}
+
+    # ---------------- e2e: autograd operator API, HOST (pinned) inputs and outputs ----------------
+    h_in = [(torch.randn(B, c, NPTS).pin_memory(), torch.randn(B, 3, NPTS).pin_memory()) for (c, r) in STAGES]
+    h_out = [torch.empty(B, c, NPTS).pin_memory() for (c, r) in STAGES]
+    voxmods = [Voxelization(r, normalize=True, eps=1e-6) for (c, r) in STAGES]
+
+    def e2e_step():
+        for (c, r), (hf, hc), ho, vm in zip(STAGES, h_in, h_out, voxmods):
+            f = hf.to(dev, non_blocking=True).requires_grad_(True)
+            x = hc.to(dev, non_blocking=True)
+            grid, nc = vm(f, x)
+            o = F.trilinear_devoxelize(grid, nc, r, True)
+            o.sum().backward()
+            ho.copy_(f.grad, non_blocking=True)
+        torch.cuda.synchronize()
+
+    e2e_steps = max(3, args.steps // 4)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0) / e2e_steps
+    h2d = sum(hf.numel() * 4 + hc.numel() * 4 for hf, hc in h_in)
+    d2h = sum(ho.numel() * 4 for ho in h_out)
+    e2e = {"value": pts_per_step / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "api": "pcfm.nn.Voxelization + pcfm.functional.trilinear_devoxelize + autograd backward, pinned host tensors in/out"}
+    del h_in, h_out
+
+    # ---------------- all-pairs CD / EMD (config 4 shapes), rows sharded over ranks ----------------
+    allpairs = None
+    try:
+        if args.skip_allpairs:
+            raise RuntimeError("skipped (--skip-allpairs)")
+        from pcfm import evaluation as ev
+        gg = torch.Generator(device=dev).manual_seed(7)
+        S = torch.randn(1000, 2048, 3, device=dev, generator=gg) * 0.3
+        R = torch.randn(1000, 2048, 3, device=dev, generator=gg) * 0.3
+        lo, hi = ev.shard_range(1000, rank, world)
+        be.chamfer3d_allpairs(S[lo:lo + 8], R[:64]); barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        cd = ev.pairwise_matrix(S[lo:hi], R, "cd", block=250)
+        a1.record(); barrier()
+        cd_ms = max_over_ranks(a0.elapsed_time(a1))
+        nref_emd = 16                                           # bounded EMD sample: 1000 x 16 pairs
+        be.emd_allpairs(S[lo:lo + 2], R[:2]); barrier()
+        a0.record()
+        emd = ev.pairwise_matrix(S[lo:hi], R[:nref_emd], "emd", block=250)
+        a1.record(); barrier()
+        emd_ms = max_over_ranks(a0.elapsed_time(a1))
+        allpairs = {"scaling": "strong", "clouds": "1000 x 1000 x 2048 pts (config 4)",
+                    "cd_pairs_per_s": 1000 * 1000 / (cd_ms * 1e-3), "cd_ms": cd_ms,
+                    "cd_evals_per_s": 1000 * 1000 * 2048 * 2048 / (cd_ms * 1e-3),
+                    "emd_pairs_per_s": 1000 * nref_emd / (emd_ms * 1e-3), "emd_ms": emd_ms,
+                    "emd_sample": f"1000 x {nref_emd} pairs", "cd_checksum": float(cd.double().sum()),
+                    "emd_checksum": float(emd.double().sum())}
+        del S, R, cd, emd
+    except Exception as e:  # noqa: BLE001
+        allpairs = {"error": repr(e)}
+
+    # ---------------- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import torch_cpu as tc
+        torch.set_num_threads(os.cpu_count() or 1)
+        feats, coords = make_cpu_inputs(torch)
+        cpu_chain_step(torch, tc, feats, coords, 2)
+        t0 = time.perf_counter()
+        pts = cpu_chain_step(torch, tc, feats, coords, B)
+        if time.perf_counter() - t0 < 8:
+            pts += cpu_chain_step(torch, tc, feats, coords, B)
+        dt = time.perf_counter() - t0
+        cpu = {"value": pts / dt / 1e6, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"one chain per stage shape (3 of the 6) at B={B}, N={NPTS}: {pts} point-passes in {dt:.1f} s; "
+                         "stock PyTorch CPU ops (scatter_add voxelize, grid_sample devoxelize, autograd backward)"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG, "clocks": clocks,
+                "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "allpairs": allpairs,
+                "lib": _lib.build_info()}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-allpairs", action="store_true", help="profiling runs: PVConv primitives only")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -30,9 +30,14 @@ def _headers_mtime():
     return max(os.path.getmtime(h) for h in hs)
 
 
+# emd.cu mirrors a reference translation unit that is built with --use_fast_math (PyTorchEMD/backend.py:20):
+# denormals are flushed there, so they are flushed here (approximate exp / division are explicit intrinsics).
+EXTRA = {"emd.cu": ["-ftz=true"]}
+
+
 def _compile(src, verbose):
     obj = os.path.join(OBJDIR, src[:-3] + ".o")
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = [NVCC] + FLAGS + EXTRA.get(src, []) + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     return src, obj, r.returncode, r.stdout + r.stderr
 

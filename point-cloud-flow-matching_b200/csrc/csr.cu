@@ -3,8 +3,9 @@
 
 namespace pcfm {
 
+static_assert(kHeavySeg >= 1, "");
 constexpr int kSmallSeg = 16;      // sorted by one thread in local memory
-constexpr int kMaxSortedSeg = 2048;  // larger segments keep their (arbitrary) arrival order
+constexpr int kMaxSortedSeg = 64;  // ranked by a warp (O(n^2/32)); longer segments keep their arrival order
 
 // One thread per edge: key, per-target count (warp-aggregated atomics: equal keys inside a warp issue ONE
 // atomicAdd), and a unique arbitrary rank inside the target's segment.
@@ -103,7 +104,8 @@ __global__ void __launch_bounds__(256) csr_finalize_kernel(const int* __restrict
                                                            const int* __restrict__ tmp,
                                                            const float* __restrict__ w, int e, int t,
                                                            int src_mod, int* __restrict__ ssrc,
-                                                           float* __restrict__ sw) {
+                                                           float* __restrict__ sw, int* __restrict__ heavy,
+                                                           int* __restrict__ nheavy, int hcap) {
   const int b = blockIdx.y;
   const long long base = (long long)b * e;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,6 +116,10 @@ __global__ void __launch_bounds__(256) csr_finalize_kernel(const int* __restrict
   if (v < t) {
     s = st[v];
     n = st[v + 1] - s;
+  }
+  if (n > kHeavySeg) {  // order of this list is irrelevant: every entry is reduced independently
+    const int slot = atomicAdd(nheavy + b, 1);
+    if (slot < hcap) heavy[(long long)b * hcap + slot] = v;
   }
   if (n >= 1 && n <= kSmallSeg) {
     int loc[kSmallSeg];
@@ -161,6 +167,8 @@ size_t csr_workspace_bytes(int b, long long e, long long t, bool weights) {
   n += align256((size_t)b * e * sizeof(int));        // tmp
   n += align256((size_t)b * e * sizeof(int));        // ssrc
   if (weights) n += align256((size_t)b * e * sizeof(float));
+  const long long hcap = e / (kHeavySeg + 1) + 1;
+  n += align256((size_t)b * hcap * sizeof(int)) + align256((size_t)b * sizeof(int));  // heavy list + counts
   return n;
 }
 
@@ -171,7 +179,11 @@ int csr_build(const int* tgt, const int* coords, int r, int* ind_out, const floa
   int* tmp = ws->take<int>((size_t)b * e);
   plan->ssrc = ws->take<int>((size_t)b * e);
   plan->sw = w ? ws->take<float>((size_t)b * e) : nullptr;
+  plan->hcap = e / (kHeavySeg + 1) + 1;  // at most this many segments can be longer than kHeavySeg
+  plan->heavy = ws->take<int>((size_t)b * plan->hcap);
+  plan->nheavy = ws->take<int>((size_t)b);
   if (!ws->ok()) return PCFM_E_WORKSPACE;
+  PCFM_CUDA(cudaMemsetAsync(plan->nheavy, 0, (size_t)b * sizeof(int), st));
   PCFM_CUDA(cudaMemsetAsync(cnt, 0, (size_t)b * t * sizeof(int), st));
   if (e > 0) {
     dim3 ge(cdiv(e, 256), b);
@@ -188,7 +200,8 @@ int csr_build(const int* tgt, const int* coords, int r, int* ind_out, const floa
     csr_fill_kernel<<<ge, 256, 0, st>>>(coords ? ind_out : tgt, rank, plan->start, e, t, tmp);
     PCFM_LAUNCHED();
     dim3 gt(cdiv(t, 256), b);
-    csr_finalize_kernel<<<gt, 256, 0, st>>>(plan->start, tmp, w, e, t, src_mod, plan->ssrc, plan->sw);
+    csr_finalize_kernel<<<gt, 256, 0, st>>>(plan->start, tmp, w, e, t, src_mod, plan->ssrc, plan->sw, plan->heavy,
+                                            plan->nheavy, plan->hcap);
     PCFM_LAUNCHED();
   }
   return 0;

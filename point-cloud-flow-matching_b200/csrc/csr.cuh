@@ -12,7 +12,12 @@ struct CsrPlan {
   int* start = nullptr;  // [B, T+1] exclusive prefix of segment sizes
   int* ssrc = nullptr;   // [B, E]   source index of the j-th sorted edge
   float* sw = nullptr;   // [B, E]   weight of the j-th sorted edge (nullptr when weights are implicit)
+  int* heavy = nullptr;  // [B, hcap] targets whose segment is longer than kHeavySeg (reduced by a whole warp)
+  int* nheavy = nullptr; // [B]
+  int hcap = 0;
 };
+
+constexpr int kHeavySeg = 16;  // segments up to this length are summed by one thread, longer ones by one warp
 
 // bytes of workspace csr_build needs (excluding `cnt`, which the caller provides: int[B,T])
 size_t csr_workspace_bytes(int b, long long e, long long t, bool weights);

@@ -10,8 +10,9 @@ namespace pcfm {
 template <int MODE, bool ROW_SMEM>
 __global__ void __launch_bounds__(1024, 1)
     row_segsum_kernel(const float* __restrict__ src, const int* __restrict__ start,
-                      const int* __restrict__ ssrc, const float* __restrict__ sw, float* __restrict__ out,
-                      int C, int S, int T, int E, int use_tma) {
+                      const int* __restrict__ ssrc, const float* __restrict__ sw,
+                      const int* __restrict__ heavy, const int* __restrict__ nheavy, int hcap,
+                      float* __restrict__ out, int C, int S, int T, int E, int use_tma) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
   const int c = blockIdx.x, b = blockIdx.y;
@@ -28,8 +29,10 @@ __global__ void __launch_bounds__(1024, 1)
   const int* ss = ssrc + (long long)b * E;
   const float* wv = (MODE == SEG_WEIGHTED) ? sw + (long long)b * E : nullptr;
   float* o = out + ((long long)b * C + c) * T;
+  // phase A: one thread per target, segments of at most kHeavySeg edges (ascending edge order)
   for (int t = threadIdx.x; t < T; t += blockDim.x) {
     const int s0 = st[t], s1 = st[t + 1];
+    if (s1 - s0 > kHeavySeg) continue;  // phase B
     float acc = 0.f;
     if (s1 > s0) {
       float rcp = 1.f;
@@ -46,6 +49,26 @@ __global__ void __launch_bounds__(1024, 1)
     }
     o[t] = acc;
   }
+  // phase B: one warp per long segment: lanes stride the segment (coalesced plan reads), fixed-shape butterfly
+  const int nh = min(nheavy[b], hcap);
+  const int* hv = heavy + (long long)b * hcap;
+  const int lane = threadIdx.x & 31;
+  for (int h = threadIdx.x >> 5; h < nh; h += blockDim.x >> 5) {
+    const int t = hv[h];
+    const int s0 = st[t], s1 = st[t + 1];
+    float rcp = 1.f;
+    if (MODE == SEG_MEAN) rcp = __frcp_rn((float)(s1 - s0));
+    float acc = 0.f;
+    for (int j = s0 + lane; j < s1; j += 32) {
+      const int si = ss[j];
+      const float f = ROW_SMEM ? smem[si] : __ldg(row_g + si);
+      if (MODE == SEG_MEAN) acc = __fadd_rn(acc, __fmul_rn(f, rcp));
+      else if (MODE == SEG_WEIGHTED) acc = __fadd_rn(acc, __fmul_rn(wv[j], f));
+      else acc = __fadd_rn(acc, f);
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) o[t] = acc;
+  }
 }
 
 template <int MODE, bool ROW_SMEM>
@@ -60,7 +83,8 @@ static int launch_segsum_t(const float* src, const CsrPlan& plan, float* out, in
     attr_set = true;
   }
   dim3 grid(c, b);
-  kern<<<grid, 1024, smem, st>>>(src, plan.start, plan.ssrc, plan.sw, out, c, s, t, e, g_opt_stage == 0);
+  kern<<<grid, 1024, smem, st>>>(src, plan.start, plan.ssrc, plan.sw, plan.heavy, plan.nheavy, plan.hcap, out, c,
+                                 s, t, e, g_opt_stage == 0);
   PCFM_LAUNCHED();
   return 0;
 }

@@ -1,0 +1,122 @@
+"""Per-op timing table (CUDA events) of the new kernels and, when oracle/_ref is built, of the UNMODIFIED reference
+CUDA kernels on the same GPU and inputs.  Test/measurement infrastructure:
+    python tests/perf_ops.py [--ref] [--only s1,chamfer] [--kind randn|uniform]
+Writes gpurun_out/perf_ops_<kind>.json."""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "point-cloud-flow-matching_b200"))
+from pcfm import _lib, backend as be  # noqa: E402
+
+
+def timeit(fn, iters=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--ref", action="store_true")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--kind", default="randn")
+    args = ap.parse_args()
+    only = set(args.only.split(",")) if args.only else None
+    ref = None
+    if args.ref:
+        from oracle import build_ref
+        ref = {k: build_ref.load_ref(k) for k in ("pvcnn", "chamfer", "emd")}
+    dev = "cuda"
+    g = torch.Generator(device=dev).manual_seed(0)
+    B, N = 8, 20000
+    rows = []
+    for name, c, r in [("s1", 128, 32), ("s2", 256, 16), ("s3", 256, 8), ("c1", 64, 32)]:
+        if only and name not in only:
+            continue
+        b, n = (2, 2048) if name == "c1" else (B, N)
+        feat = torch.randn(b, c, n, device=dev, generator=g)
+        if args.kind == "randn":
+            coords = torch.randn(b, 3, n, device=dev, generator=g)
+        else:  # uniform cube: flat occupancy
+            coords = torch.rand(b, 3, n, device=dev, generator=g) * 2 - 1
+        nc = coords - coords.mean(2, keepdim=True)
+        nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 1e-6) + 0.5
+        nc = torch.clamp(nc * r, 0, r - 1).contiguous()
+        vox = torch.round(nc).to(torch.int32).contiguous()
+        grid = torch.randn(b, c, r ** 3, device=dev, generator=g)
+        gy = torch.randn(b, c, n, device=dev, generator=g)
+        P = be.pvcnn
+        out, ind, cnt = P.avg_voxelize_forward(feat, vox, r)
+        outs, inds, wgts = P.trilinear_devoxelize_forward(r, True, nc, grid)
+        s = r ** 3
+        byt = {"vox_fwd": 4 * b * (c * n + 3 * n + c * s + n + s), "vox_bwd": 4 * b * (c * s + n + s + c * n),
+               "devox_fwd": 4 * b * (3 * n + c * s + c * n + 16 * n), "devox_bwd": 4 * b * (c * n + 16 * n + c * s)}
+        ops = {
+            "vox_fwd": lambda: P.avg_voxelize_forward(feat, vox, r),
+            "vox_bwd": lambda: P.avg_voxelize_backward(grid, ind, cnt),
+            "devox_fwd": lambda: P.trilinear_devoxelize_forward(r, True, nc, grid),
+            "devox_fwd_eval": lambda: P.trilinear_devoxelize_forward(r, False, nc, grid),
+            "devox_bwd": lambda: P.trilinear_devoxelize_backward(gy, inds, wgts, r),
+        }
+        for op, fn in ops.items():
+            ms = timeit(fn)
+            row = {"shape": name, "C": c, "r": r, "B": b, "N": n, "op": op, "ms": round(ms, 4),
+                   "max_cnt": int(cnt.max()), "occupied": int((cnt > 0).sum())}
+            if op in byt:
+                row["GBps"] = round(byt[op] / ms / 1e6, 1)
+                row["frac_of_6545"] = round(byt[op] / ms / 1e6 / 6545.3, 4)
+            if op == "vox_fwd":
+                _lib.set_option("vox_fwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4); _lib.set_option("vox_fwd", 0)
+            if op == "devox_bwd":
+                _lib.set_option("devox_bwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4); _lib.set_option("devox_bwd", 0)
+            if op in ("vox_fwd", "devox_fwd"):
+                _lib.set_option("stage", 1); row["ms_plain_stage"] = round(timeit(fn), 4); _lib.set_option("stage", 0)
+            if ref and ref["pvcnn"] is not None:
+                R = ref["pvcnn"]
+                rf = {"vox_fwd": lambda: R.avg_voxelize_forward(feat, vox, r),
+                      "vox_bwd": lambda: R.avg_voxelize_backward(grid, ind, cnt),
+                      "devox_fwd": lambda: R.trilinear_devoxelize_forward(r, True, nc, grid),
+                      "devox_fwd_eval": lambda: R.trilinear_devoxelize_forward(r, False, nc, grid),
+                      "devox_bwd": lambda: R.trilinear_devoxelize_backward(gy, inds, wgts, r)}[op]
+                row["ms_reference_cuda"] = round(timeit(rf, iters=3, warm=1), 3)
+            rows.append(row)
+            print(json.dumps(row), flush=True)
+    if not only or "chamfer" in only:
+        for (b, n, m) in [(32, 2000, 1000), (2, 2048, 2048), (8, 20000, 20000)]:
+            a = torch.rand(b, n, 3, device=dev, generator=g); c2 = torch.rand(b, m, 3, device=dev, generator=g)
+            d1 = torch.zeros(b, n, device=dev); d2 = torch.zeros(b, m, device=dev)
+            i1 = torch.zeros(b, n, dtype=torch.int32, device=dev); i2 = torch.zeros(b, m, dtype=torch.int32, device=dev)
+            row = {"op": "chamfer_fwd", "B": b, "N": n, "M": m,
+                   "ms": round(timeit(lambda: be.chamfer.forward(a, c2, d1, d2, i1, i2)), 4)}
+            row["Gevals_per_s"] = round(2 * b * n * m / row["ms"] / 1e6, 1)
+            if ref and ref["chamfer"] is not None:
+                row["ms_reference_cuda"] = round(timeit(lambda: ref["chamfer"].forward(a, c2, d1, d2, i1, i2), iters=3, warm=1), 3)
+            rows.append(row); print(json.dumps(row), flush=True)
+    if not only or "emd" in only:
+        for (b, n) in [(8, 1024), (32, 2048)]:
+            a = torch.rand(b, n, 3, device=dev, generator=g); c2 = torch.rand(b, n, 3, device=dev, generator=g)
+            row = {"op": "emd_approxmatch+matchcost", "B": b, "N": n}
+            row["ms"] = round(timeit(lambda: be.emd.matchcost_forward(a, c2, be.emd.approxmatch_forward(a, c2)), iters=3, warm=1), 3)
+            if ref and ref["emd"] is not None:
+                E = ref["emd"]
+                row["ms_reference_cuda"] = round(timeit(lambda: E.matchcost_forward(a, c2, E.approxmatch_forward(a, c2)), iters=3, warm=1), 3)
+            rows.append(row); print(json.dumps(row), flush=True)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", f"perf_ops_{args.kind}.json"), "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
