@@ -212,7 +212,7 @@ def run_ours(args):
             if ev: ev[1].record()
             outs, inds, wgts = P.trilinear_devoxelize_forward(ch["r"], True, ch["nc"], ch["conv_out"])
             if ev: ev[2].record()
-            ggrid = P.trilinear_devoxelize_backward(ch["gy"], inds, wgts, ch["r"])
+            ggrid = P.trilinear_devoxelize_backward_coords(ch["gy"], ch["nc"], ch["r"])  # what the autograd op calls
             if ev: ev[3].record()
             gfeat = P.avg_voxelize_backward(ch["gconv"], ind, cnt)
             if ev:

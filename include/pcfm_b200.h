@@ -42,8 +42,8 @@ const char* pcfm_build_info(void);
 int64_t pcfm_launch_count(void);
 void pcfm_reset_launch_count(void);
 /* Tuning knob: "variant" selects alternative kernel implementations for A/B measurement.
- * key: "devox_bwd" (0 = sorted-CSR gather [default], 1 = global RED atomics),
- *      "vox_fwd"   (0 = sorted-CSR gather [default], 1 = global RED atomics),
+ * key: "devox_bwd" (generic inds/wgts entry: 0 = sorted-segment gather [default], 1 = global RED atomics),
+ *      "vox_fwd"   (0 = cell plan [default], 1 = global RED atomics, 2 = generic sorted-segment gather),
  *      "stage"     (0 = TMA bulk staging where aligned [default], 1 = plain ld/st staging). */
 int pcfm_set_option(const char* key, int value);
 
@@ -87,6 +87,16 @@ size_t pcfm_trilinear_devoxelize_backward_workspace(int b, int c, int n, int r);
 int pcfm_trilinear_devoxelize_backward(const float* grad_y, const int* inds, const float* wgts,
                                        int b, int c, int n, int r, float* grad_x,
                                        void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
+
+/* Same result as pcfm_trilinear_devoxelize_backward for the inds/wgts that pcfm_trilinear_devoxelize_forward derives
+ * from `coords` (f32[B,3,N] in [0,r-1]), but takes the coordinates themselves: the 8 weights are recomputed with the
+ * forward's exact arithmetic and every point is visited once per channel (cell-sorted plan, no atomics).  This is the
+ * entry the autograd wrapper uses (it saves `coords` next to the reference's inds/wgts).  Requires r^3 floats to fit
+ * in shared memory (r <= 37); returns PCFM_E_BADARG otherwise (use the generic entry above). */
+size_t pcfm_trilinear_devoxelize_backward_coords_workspace(int b, int c, int n, int r);
+int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* coords, int b, int c, int n, int r,
+                                              float* grad_x, void* workspace, size_t workspace_bytes,
+                                              pcfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ball query / grouping / gather / FPS / 3-NN  (src/ball_query, src/grouping, src/sampling,

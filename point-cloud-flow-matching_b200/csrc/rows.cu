@@ -262,26 +262,21 @@ extern "C" {
 // ---------------------------------------------------------------------------------------------
 // avg_voxelize
 // ---------------------------------------------------------------------------------------------
-size_t pcfm_avg_voxelize_forward_workspace(int b, int c, int n, int r) {
-  (void)c;
-  if (b <= 0 || n < 0 || r <= 0) return 0;
-  return csr_workspace_bytes(b, n, (long long)r * r * r, false) + 256;
-}
+}  // extern "C"
 
-int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, int c, int n, int r, float* out,
-                              int* ind, int* cnt, void* workspace, size_t workspace_bytes,
-                              pcfm_stream_t stream) {
-  if (b < 0 || c < 0 || n < 0 || r <= 0 || (long long)r * r * r > 0x7fffffffLL) return PCFM_E_BADARG;
-  if (b == 0) return 0;
-  if (!coords || !ind || !cnt || (c > 0 && (!features || !out))) return PCFM_E_BADARG;
-  cudaStream_t st = (cudaStream_t)stream;
+namespace pcfm {
+// A/B variants of avg_voxelize forward kept for measurement (pcfm_set_option("vox_fwd", v)):
+//   1 = the reference's formulation (global fp32 atomics) on a full grid, 2 = generic sorted-segment engine
+int avg_voxelize_forward_generic(const float* features, const int* coords, int b, int c, int n, int r, float* out,
+                                 int* ind, int* cnt, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                                 int variant) {
   const int s = r * r * r;
   Workspace ws(workspace, workspace_bytes);
   CsrPlan plan;
   int rc = csr_build(nullptr, coords, r, ind, nullptr, b, n, s, n > 0 ? n : 1, cnt, &plan, &ws, st);
   if (rc) return rc;
   if (c == 0) return 0;
-  if (g_opt_vox_fwd == 1) {
+  if (variant == 1) {
     PCFM_CUDA(cudaMemsetAsync(out, 0, (size_t)b * c * s * sizeof(float), st));
     if (n > 0) {
       dim3 grid(cdiv(n, 256), c, b);
@@ -292,6 +287,9 @@ int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, i
   }
   return launch_row_segsum(SEG_MEAN, features, plan, out, b, c, n, s, n, st);
 }
+}  // namespace pcfm
+
+extern "C" {
 
 size_t pcfm_avg_voxelize_backward_workspace(int b, int c, int n, int s) {
   (void)c; (void)s;

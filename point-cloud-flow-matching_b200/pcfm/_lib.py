@@ -31,6 +31,8 @@ SIGNATURES = {
     "pcfm_trilinear_devoxelize_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "pcfm_trilinear_devoxelize_backward_workspace": (_sz, [_i, _i, _i, _i]),
     "pcfm_trilinear_devoxelize_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_trilinear_devoxelize_backward_coords_workspace": (_sz, [_i, _i, _i, _i]),
+    "pcfm_trilinear_devoxelize_backward_coords": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_ball_query": (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _p]),
     "pcfm_grouping_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pcfm_grouping_backward_workspace": (_sz, [_i, _i, _i, _i, _i]),

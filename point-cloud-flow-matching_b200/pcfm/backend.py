@@ -130,6 +130,25 @@ class _PvcnnBackend:
                   "trilinear_devoxelize_backward")
         return grad_x
 
+    MAX_FAST_DEVOX_BWD_R = 37  # r^3 floats must fit in shared memory for the cell-plan kernel
+
+    @staticmethod
+    def trilinear_devoxelize_backward_coords(grad_y, coords, r):
+        """Extension (not in the reference module): backward from the float coordinates instead of inds/wgts.
+        Same values as trilinear_devoxelize_backward(grad_y, *forward(coords)[1:], r); every point is visited once."""
+        _chk(grad_y, "grad_y", "f")
+        _chk(coords, "coords", "f")
+        b, c, n = grad_y.shape
+        r = int(r)
+        dev = grad_y.device
+        grad_x = torch.empty((b, c, r * r * r), dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            ws = _ws(lib.pcfm_trilinear_devoxelize_backward_coords_workspace(b, c, n, r), dev)
+            check(lib.pcfm_trilinear_devoxelize_backward_coords(_ptr(grad_y), _ptr(coords), b, c, n, r, _ptr(grad_x),
+                                                                _ptr(ws), ws.numel(), _stream(grad_y)),
+                  "trilinear_devoxelize_backward_coords")
+        return grad_x
+
     # ---- ball query (ball_query.cpp:6-30) ----
     @staticmethod
     def ball_query(centers_coords, points_coords, radius, num_neighbors):

@@ -43,18 +43,22 @@ class TrilinearDevoxelization(Function):
     def forward(ctx, features, coords, resolution, is_training=True):
         b, c = features.shape[0], features.shape[1]
         grid = features.contiguous().view(b, c, -1)
-        outs, inds, wgts = _backend.trilinear_devoxelize_forward(int(resolution), bool(is_training),
-                                                                 coords.contiguous(), grid)
+        coords = coords.contiguous()
+        outs, inds, wgts = _backend.trilinear_devoxelize_forward(int(resolution), bool(is_training), coords, grid)
         if is_training:
-            ctx.save_for_backward(inds, wgts)
+            # inds / wgts are saved like the reference does; the coordinates ride along for the cell-plan backward
+            ctx.save_for_backward(inds, wgts, coords)
             ctx.r = int(resolution)
         return outs
 
     @staticmethod
     def backward(ctx, grad_output):
-        inds, wgts = ctx.saved_tensors  # eval mode saved nothing: unpacking fails, as in the reference
+        inds, wgts, coords = ctx.saved_tensors  # eval mode saved nothing: unpacking fails, as in the reference
         r = ctx.r
-        g = _backend.trilinear_devoxelize_backward(grad_output.contiguous(), inds, wgts, r)
+        if r <= _backend.MAX_FAST_DEVOX_BWD_R:
+            g = _backend.trilinear_devoxelize_backward_coords(grad_output.contiguous(), coords, r)
+        else:
+            g = _backend.trilinear_devoxelize_backward(grad_output.contiguous(), inds, wgts, r)
         return g.view(grad_output.shape[0], grad_output.shape[1], r, r, r), None, None, None
 
 

@@ -69,7 +69,8 @@ def main():
             "vox_bwd": lambda: P.avg_voxelize_backward(grid, ind, cnt),
             "devox_fwd": lambda: P.trilinear_devoxelize_forward(r, True, nc, grid),
             "devox_fwd_eval": lambda: P.trilinear_devoxelize_forward(r, False, nc, grid),
-            "devox_bwd": lambda: P.trilinear_devoxelize_backward(gy, inds, wgts, r),
+            "devox_bwd": lambda: P.trilinear_devoxelize_backward_coords(gy, nc, r),
+            "devox_bwd_generic": lambda: P.trilinear_devoxelize_backward(gy, inds, wgts, r),
         }
         for op, fn in ops.items():
             ms = timeit(fn)
@@ -79,8 +80,9 @@ def main():
                 row["GBps"] = round(byt[op] / ms / 1e6, 1)
                 row["frac_of_6545"] = round(byt[op] / ms / 1e6 / 6545.3, 4)
             if op == "vox_fwd":
-                _lib.set_option("vox_fwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4); _lib.set_option("vox_fwd", 0)
-            if op == "devox_bwd":
+                _lib.set_option("vox_fwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4)
+                _lib.set_option("vox_fwd", 2); row["ms_csr_variant"] = round(timeit(fn), 4); _lib.set_option("vox_fwd", 0)
+            if op == "devox_bwd_generic":
                 _lib.set_option("devox_bwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4); _lib.set_option("devox_bwd", 0)
             if op in ("vox_fwd", "devox_fwd"):
                 _lib.set_option("stage", 1); row["ms_plain_stage"] = round(timeit(fn), 4); _lib.set_option("stage", 0)
@@ -90,7 +92,8 @@ def main():
                       "vox_bwd": lambda: R.avg_voxelize_backward(grid, ind, cnt),
                       "devox_fwd": lambda: R.trilinear_devoxelize_forward(r, True, nc, grid),
                       "devox_fwd_eval": lambda: R.trilinear_devoxelize_forward(r, False, nc, grid),
-                      "devox_bwd": lambda: R.trilinear_devoxelize_backward(gy, inds, wgts, r)}[op]
+                      "devox_bwd": lambda: R.trilinear_devoxelize_backward(gy, inds, wgts, r),
+                      "devox_bwd_generic": lambda: R.trilinear_devoxelize_backward(gy, inds, wgts, r)}[op]
                 row["ms_reference_cuda"] = round(timeit(rf, iters=3, warm=1), 3)
             rows.append(row)
             print(json.dumps(row), flush=True)

@@ -18,7 +18,7 @@ def main():
     for (b, c, n, r) in [(2, 8, 1001, 7), (1, 16, 3000, 16), (2, 4, 2048, 32), (1, 2, 60000, 4)]:
         feat = rn(b, c, n)
         vc = torch.randint(0, r, (b, 3, n), device="cuda", dtype=torch.int32, generator=g)
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             _lib.set_option("vox_fwd", variant)
             out, ind, cnt = be.pvcnn.avg_voxelize_forward(feat, vc, r)
         _lib.set_option("vox_fwd", 0)
@@ -34,6 +34,10 @@ def main():
             _lib.set_option("devox_bwd", variant)
             be.pvcnn.trilinear_devoxelize_backward(rn(b, c, n), inds, wgts, r)
         _lib.set_option("devox_bwd", 0)
+        for stage in (0, 1):
+            _lib.set_option("stage", stage)
+            be.pvcnn.trilinear_devoxelize_backward_coords(rn(b, c, n), fc, r)
+        _lib.set_option("stage", 0)
     # plane too large for shared memory (r = 40 -> 64000 floats): L2 path
     be.pvcnn.trilinear_devoxelize_forward(40, True, torch.rand(1, 3, 500, device="cuda") * 39, rn(1, 2, 64000))
     pts = torch.rand(2, 3, 700, device="cuda", generator=g)
