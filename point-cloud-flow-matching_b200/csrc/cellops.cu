@@ -59,10 +59,17 @@ __global__ void __launch_bounds__(1024, 2)
     const int s0 = sl[ci];
     const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
     float acc = 0.f;
-    for (int i = 0; i < n; ++i) {
-      const int p = rc[s0 + 32 * i];
-      const float f = ROW_SMEM ? smem[p] : __ldg(row_g + p);
-      acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
+    for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread
+      int p[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) p[k] = (i0 + k < n) ? rc[s0 + 32 * (i0 + k)] : -1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (p[k] >= 0) {
+          const float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
+          acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
+        }
+      }
     }
     o[t] = acc;
   }
@@ -150,7 +157,8 @@ __global__ void __launch_bounds__(1024, 1)
     for (uint32_t off = 0; off < (uint32_t)bulk * 4u; off += kBulkChunk)
       bulk_g2s((char*)row + off, (const char*)row_g + off, min(kBulkChunk, (uint32_t)bulk * 4u - off), &bar);
   }
-  for (int i = threadIdx.x; i < P; i += blockDim.x) plane[i] = 0.f;  // overlaps the row copy
+  for (int i = threadIdx.x; i < ((P + 3) >> 2); i += blockDim.x)  // overlaps the row copy
+    ((float4*)plane)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ROW_SMEM) {
     for (int i = bulk + threadIdx.x; i < N; i += blockDim.x) row[i] = __ldg(row_g + i);
     if (bulk > 0) mbar_wait(&bar, 0);
@@ -171,14 +179,21 @@ __global__ void __launch_bounds__(1024, 1)
       const int n = d >> 24;
       cell = d & 0xffffff;
       const int s0 = sl[ci];
-      for (int i = 0; i < n; ++i) {
-        const float4 q = rc[s0 + 32 * i];
-        const int p = __float_as_int(q.x);
-        const float g = ROW_SMEM ? row[p] : __ldg(row_g + p);
-        float w[8];
-        tri_weights(q.y, q.z, q.w, w);
+      for (int i0 = 0; i0 < n; i0 += 2) {  // two independent record loads in flight per thread
+        float4 q[2];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s[k] = __fadd_rn(s[k], __fmul_rn(w[k], g));  // trilinear_devox.cu:152-159
+        for (int k = 0; k < 2; ++k)
+          q[k] = (i0 + k < n) ? rc[s0 + 32 * (i0 + k)] : make_float4(__int_as_float(-1), 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int p = __float_as_int(q[u].x);
+          if (p < 0) continue;
+          const float g = ROW_SMEM ? row[p] : __ldg(row_g + p);
+          float w[8];
+          tri_weights(q[u].y, q[u].z, q[u].w, w);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) s[k] = __fadd_rn(s[k], __fmul_rn(w[k], g));  // trilinear_devox.cu:152-159
+        }
       }
     }
     PCFM_CORNER_PHASES(active, cell, s)
@@ -226,7 +241,7 @@ __global__ void __launch_bounds__(1024, 1)
       for (uint32_t off = 0; off < (uint32_t)P * 4u; off += kBulkChunk)
         bulk_s2g((char*)o + off, (const char*)plane + off, min(kBulkChunk, (uint32_t)P * 4u - off));
       bulk_commit();
-      bulk_wait_all();
+      bulk_wait_read();  // the CTA may exit once the source has been read out of shared memory
     }
   } else {
     for (int i = threadIdx.x; i < P; i += blockDim.x) o[i] = plane[i];
@@ -327,12 +342,14 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
   }
   dim3 grid(c, b);
   const bool row_smem = devox_bwd_smem(n, r, true) <= kSmemLimit;
+  // small planes (r <= 16): two CTAs of 512 threads per SM overlap one CTA's staging with the other's compute
+  const int threads = (row_smem && devox_bwd_smem(n, r, true) <= 110 * 1024) ? 512 : 1024;
   if (row_smem)
-    devox_bwd_cell_kernel<true><<<grid, 1024, devox_bwd_smem(n, r, true), st>>>(
+    devox_bwd_cell_kernel<true><<<grid, threads, devox_bwd_smem(n, r, true), st>>>(
         grad_y, plan.cells, plan.slot0, plan.nlight, plan.heavy, plan.nheavy, (const float4*)plan.rec, grad_x, c, n,
         r, plan.lcap, plan.hcap, plan.rcap, g_opt_stage == 0);
   else
-    devox_bwd_cell_kernel<false><<<grid, 1024, devox_bwd_smem(n, r, false), st>>>(
+    devox_bwd_cell_kernel<false><<<grid, threads, devox_bwd_smem(n, r, false), st>>>(
         grad_y, plan.cells, plan.slot0, plan.nlight, plan.heavy, plan.nheavy, (const float4*)plan.rec, grad_x, c, n,
         r, plan.lcap, plan.hcap, plan.rcap, g_opt_stage == 0);
   PCFM_LAUNCHED();

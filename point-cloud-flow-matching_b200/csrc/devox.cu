@@ -7,15 +7,26 @@
 
 namespace pcfm {
 
-template <int G, bool PLANE_SMEM>
+// Shared-memory plane layout: x-layer `x` of plane `g` starts at ((g*(r+1) + x) * sx) floats, sx = r*r + 4.
+//   * every layer is one 16-byte-aligned TMA bulk copy (r*r floats),
+//   * the +4 skew moves consecutive x-layers by four banks (the unpadded layout maps a voxel to bank z only, and a
+//     centred cloud then fights over a handful of banks: 6-way conflicts measured on Gaussian clouds),
+//   * layer r of every plane is a zeroed guard, so the 8 corners can always be read at the CONSTANT offsets
+//     {0,1} + {0,r} + {0,sx}: a corner beyond the grid (or beyond a lattice plane) carries weight exactly 0
+//     (trilinear_devox.cu:64-75 skips it by not offsetting the index), and 0 * finite = 0.
+template <int G, int RT, bool PLANE_SMEM>
 __global__ void __launch_bounds__(1024, 1)
     devox_fwd_kernel(const float* __restrict__ coords, const float* __restrict__ feat,
                      float* __restrict__ outs, int* __restrict__ inds, float* __restrict__ wgts, int C, int n,
-                     int r, int training, int use_tma) {
+                     int r_rt, int training, int use_tma) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
+  const int r = RT > 0 ? RT : r_rt;
   const int c0 = blockIdx.x * G, b = blockIdx.y;
   const int r2 = r * r, P = r2 * r;
+  const int sx = PLANE_SMEM ? r2 + 4 : r2;   // layer stride
+  // plane stride: r layers + guard; the farthest corner read is r*sx + r*r + r floats from the plane base
+  const int sp = PLANE_SMEM ? ((r + 1) * sx + r + 3) & ~3 : P;
   const float* pg = feat + ((long long)b * C + c0) * P;
   if (PLANE_SMEM) {
     if (threadIdx.x == 0) {
@@ -23,7 +34,32 @@ __global__ void __launch_bounds__(1024, 1)
       fence_mbar_init();
     }
     __syncthreads();
-    stage_floats(smem, pg, G * P, &bar, 0, use_tma != 0);
+    const bool bulk = use_tma && ((r2 & 3) == 0) && ((((uintptr_t)pg) & 15) == 0);
+    if (bulk) {
+      if (threadIdx.x == 0) mbar_arrive_expect_tx(&bar, (uint32_t)(G * P) * 4u);
+      __syncthreads();  // expect_tx is armed before any copy can complete
+      for (int l = threadIdx.x; l < G * r; l += blockDim.x) {   // one bulk copy per x-layer, issued by G*r threads
+        const int g = l / r, x = l - g * r;
+        bulk_g2s(smem + (size_t)g * sp + (size_t)x * sx, pg + (size_t)g * P + (size_t)x * r2, (uint32_t)r2 * 4u, &bar);
+      }
+    } else {
+      for (int i = threadIdx.x; i < G * P; i += blockDim.x) {
+        const int g = i / P, rem = i - g * P, x = rem / r2;
+        smem[(size_t)g * sp + (size_t)x * sx + (rem - x * r2)] = __ldg(pg + i);
+      }
+    }
+    // zero the 4-float skew of every layer and the guard layer of every plane (never written by the copies)
+    for (int i = threadIdx.x; i < G * r * 4; i += blockDim.x) {
+      const int l = i >> 2, g = l / r, x = l - g * r;
+      smem[(size_t)g * sp + (size_t)x * sx + r2 + (i & 3)] = 0.f;
+    }
+    const int guard = sp - r * sx;
+    for (int i = threadIdx.x; i < G * guard; i += blockDim.x) {
+      const int g = i / guard;
+      smem[(size_t)g * sp + (size_t)r * sx + (i - g * guard)] = 0.f;
+    }
+    if (bulk) mbar_wait(&bar, 0);
+    __syncthreads();
   }
   const float* cb = coords + (long long)b * 3 * n;
   float* ob = outs + ((long long)b * C + c0) * n;
@@ -48,57 +84,83 @@ __global__ void __launch_bounds__(1024, 1)
     w[5] = __fmul_rn(__fmul_rn(x1, y0), z1);
     w[6] = __fmul_rn(__fmul_rn(x1, y1), z0);
     w[7] = __fmul_rn(__fmul_rn(x1, y1), z1);
-    const int ox = (x1 > 0.f) ? r2 : 0, oy = (y1 > 0.f) ? r : 0, oz = (z1 > 0.f) ? 1 : 0;
-    int id[8];
-    id[0] = (int)xl * r2 + (int)yl * r + (int)zl;
-    id[1] = id[0] + oz;
-    id[2] = id[0] + oy;
-    id[3] = id[2] + oz;
-    id[4] = id[0] + ox;
-    id[5] = id[4] + oz;
-    id[6] = id[4] + oy;
-    id[7] = id[6] + oz;
-    if (save) {
+    const int xi = (int)xl, yi = (int)yl, zi = (int)zl;
+    if (save) {  // the reference's index rule, written once per batch element (trilinear_devox.cu:64-94)
+      const int ox = (x1 > 0.f) ? r2 : 0, oy = (y1 > 0.f) ? r : 0, oz = (z1 > 0.f) ? 1 : 0;
+      const int i0 = xi * r2 + yi * r + zi;
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        ib[(long long)k * n + i] = id[k];
+        ib[(long long)k * n + i] = i0 + ((k & 4) ? ox : 0) + ((k & 2) ? oy : 0) + ((k & 1) ? oz : 0);
         wb[(long long)k * n + i] = w[k];
       }
     }
+    if (PLANE_SMEM) {
+      const float* p0 = smem + (xi * sx + yi * r + zi);
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float acc;
-      if (PLANE_SMEM) {
-        const float* pl = smem + g * P;
-        acc = w[0] * pl[id[0]];
-#pragma unroll
-        for (int k = 1; k < 8; ++k) acc = fmaf(w[k], pl[id[k]], acc);
-      } else {
-        const float* pl = pg + (long long)g * P;
-        acc = w[0] * __ldg(pl + id[0]);
-#pragma unroll
-        for (int k = 1; k < 8; ++k) acc = fmaf(w[k], __ldg(pl + id[k]), acc);
+      for (int g = 0; g < G; ++g) {
+        const float* pl = p0 + g * sp;
+        float acc = w[0] * pl[0];
+        acc = fmaf(w[1], pl[1], acc);
+        acc = fmaf(w[2], pl[r], acc);
+        acc = fmaf(w[3], pl[r + 1], acc);
+        acc = fmaf(w[4], pl[sx], acc);
+        acc = fmaf(w[5], pl[sx + 1], acc);
+        acc = fmaf(w[6], pl[sx + r], acc);
+        acc = fmaf(w[7], pl[sx + r + 1], acc);
+        ob[(long long)g * n + i] = acc;
       }
-      ob[(long long)g * n + i] = acc;
+    } else {
+      // plane does not fit in shared memory: read through L2 with the reference's in-range indices
+      const int ox = (x1 > 0.f) ? r2 : 0, oy = (y1 > 0.f) ? r : 0, oz = (z1 > 0.f) ? 1 : 0;
+      const int i0 = xi * r2 + yi * r + zi;
+#pragma unroll
+      for (int g = 0; g < G; ++g) {
+        const float* pl = pg + (long long)g * P + i0;
+        float acc = w[0] * __ldg(pl);
+        acc = fmaf(w[1], __ldg(pl + oz), acc);
+        acc = fmaf(w[2], __ldg(pl + oy), acc);
+        acc = fmaf(w[3], __ldg(pl + oy + oz), acc);
+        acc = fmaf(w[4], __ldg(pl + ox), acc);
+        acc = fmaf(w[5], __ldg(pl + ox + oz), acc);
+        acc = fmaf(w[6], __ldg(pl + ox + oy), acc);
+        acc = fmaf(w[7], __ldg(pl + ox + oy + oz), acc);
+        ob[(long long)g * n + i] = acc;
+      }
     }
   }
 }
 
-template <int G, bool PLANE_SMEM>
+static size_t devox_fwd_smem(int g, int r) {
+  const size_t sx = (size_t)r * r + 4;
+  return (size_t)g * (((r + 1) * sx + r + 3) & ~(size_t)3) * sizeof(float);
+}
+constexpr size_t kDevoxSmemLimit = 227 * 1024 - 512;
+
+template <int G, int RT, bool PLANE_SMEM>
 static int launch_devox_t(const float* coords, const float* feat, float* outs, int* inds, float* wgts, int b,
                           int c, int n, int r, int training, cudaStream_t st) {
   static bool attr_set = false;
-  auto kern = devox_fwd_kernel<G, PLANE_SMEM>;
-  const size_t smem = PLANE_SMEM ? (size_t)G * r * r * r * sizeof(float) : 0;
+  auto kern = devox_fwd_kernel<G, RT, PLANE_SMEM>;
+  const size_t smem = PLANE_SMEM ? devox_fwd_smem(G, r) : 0;
   if (!attr_set) {
-    PCFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kMaxStageFloats * sizeof(float))));
+    PCFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDevoxSmemLimit));
     attr_set = true;
   }
   dim3 grid(c / G, b);
-  kern<<<grid, 1024, smem, st>>>(coords, feat, outs, inds, wgts, c, n, r, training, g_opt_stage == 0);
+  // two CTAs per SM when the planes are small (56+ registers: 512 threads each), else one CTA of 1024 threads
+  const int threads = (PLANE_SMEM && smem <= 110 * 1024) ? 512 : 1024;
+  kern<<<grid, threads, smem, st>>>(coords, feat, outs, inds, wgts, c, n, r, training, g_opt_stage == 0);
   PCFM_LAUNCHED();
   return 0;
+}
+
+// channels per CTA: as many as fit in ~100 KB (two CTAs per SM) while keeping the grid at >= 2 CTAs per SM
+static int devox_group(int b, int c, int r) {
+  if (devox_fwd_smem(1, r) > kDevoxSmemLimit) return 0;
+  int g = 8;
+  while (g > 1 && (c % g != 0 || devox_fwd_smem(g, r) > 100 * 1024 || (long long)(c / g) * b < 2LL * num_sms()))
+    g >>= 1;
+  return g;
 }
 
 // inds/wgts only (C == 0 or nothing else to do)
@@ -150,12 +212,19 @@ extern "C" int pcfm_trilinear_devoxelize_forward(const float* coords, const floa
     }
     return 0;
   }
-  const int p = r * r * r;
-  switch (pick_group(b, c, p)) {
-    case 0: return launch_devox_t<1, false>(coords, features, outs, inds, wgts, b, c, n, r, is_training, st);
-    case 8: return launch_devox_t<8, true>(coords, features, outs, inds, wgts, b, c, n, r, is_training, st);
-    case 4: return launch_devox_t<4, true>(coords, features, outs, inds, wgts, b, c, n, r, is_training, st);
-    case 2: return launch_devox_t<2, true>(coords, features, outs, inds, wgts, b, c, n, r, is_training, st);
-    default: return launch_devox_t<1, true>(coords, features, outs, inds, wgts, b, c, n, r, is_training, st);
+#define PCFM_DEVOX(G, RT) return launch_devox_t<G, RT, true>(coords, features, outs, inds, wgts, b, c, n, r, is_training, st)
+  const int g = devox_group(b, c, r);
+  if (g == 0) return launch_devox_t<1, 0, false>(coords, features, outs, inds, wgts, b, c, n, r, is_training, st);
+  if (r == 32 && g == 1) PCFM_DEVOX(1, 32);
+  if (r == 16 && g == 4) PCFM_DEVOX(4, 16);
+  if (r == 16 && g == 2) PCFM_DEVOX(2, 16);
+  if (r == 8 && g == 8) PCFM_DEVOX(8, 8);
+  if (r == 8 && g == 4) PCFM_DEVOX(4, 8);
+  switch (g) {
+    case 8: PCFM_DEVOX(8, 0);
+    case 4: PCFM_DEVOX(4, 0);
+    case 2: PCFM_DEVOX(2, 0);
+    default: PCFM_DEVOX(1, 0);
   }
+#undef PCFM_DEVOX
 }

@@ -33,6 +33,9 @@ def main():
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--only", default="")
     ap.add_argument("--kind", default="randn")
+    ap.add_argument("--ops", default="")
+    ap.add_argument("--no-variants", action="store_true")
+    ap.add_argument("--iters", type=int, default=10)
     args = ap.parse_args()
     only = set(args.only.split(",")) if args.only else None
     ref = None
@@ -72,13 +75,18 @@ def main():
             "devox_bwd": lambda: P.trilinear_devoxelize_backward_coords(gy, nc, r),
             "devox_bwd_generic": lambda: P.trilinear_devoxelize_backward(gy, inds, wgts, r),
         }
+        if args.ops:
+            ops = {k: v for k, v in ops.items() if k in args.ops.split(",")}
         for op, fn in ops.items():
-            ms = timeit(fn)
+            ms = timeit(fn, iters=args.iters)
             row = {"shape": name, "C": c, "r": r, "B": b, "N": n, "op": op, "ms": round(ms, 4),
                    "max_cnt": int(cnt.max()), "occupied": int((cnt > 0).sum())}
             if op in byt:
                 row["GBps"] = round(byt[op] / ms / 1e6, 1)
                 row["frac_of_6545"] = round(byt[op] / ms / 1e6 / 6545.3, 4)
+            if args.no_variants:
+                rows.append(row); print(json.dumps(row), flush=True)
+                continue
             if op == "vox_fwd":
                 _lib.set_option("vox_fwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4)
                 _lib.set_option("vox_fwd", 2); row["ms_csr_variant"] = round(timeit(fn), 4); _lib.set_option("vox_fwd", 0)
