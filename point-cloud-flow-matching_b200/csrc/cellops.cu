@@ -15,8 +15,8 @@ namespace pcfm {
 template <bool ROW_SMEM>
 __global__ void __launch_bounds__(1024, 2)
     vox_fwd_cell_kernel(const float* __restrict__ feat, const int* __restrict__ cells,
-                        const int* __restrict__ slot0, const int* __restrict__ nlight,
-                        const int* __restrict__ heavy, const int* __restrict__ nheavy,
+                        const int* __restrict__ slot0, const int* __restrict__ meta,
+                        const int* __restrict__ heavy,
                         const int* __restrict__ rec, float* __restrict__ out, int C, int N, int T, int lcap,
                         int hcap, int rcap, int use_tma) {
   extern __shared__ __align__(128) float smem[];
@@ -52,11 +52,12 @@ __global__ void __launch_bounds__(1024, 2)
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
   const int* rc = rec + (long long)b * rcap;
-  const int nl = nlight[b];
+  const int nl = meta[b * kMetaInts + 15];  // mean plans use a single class: [0, lend[7])
   for (int ci = threadIdx.x; ci < nl; ci += blockDim.x) {
     const int d = cl[ci];
     const int n = d >> 24, t = d & 0xffffff;
-    const int s0 = sl[ci];
+    if (n == 0) continue;  // alignment hole
+    const int s0 = sl[ci] & 0xffffff;
     const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
     float acc = 0.f;
     for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread
@@ -73,17 +74,22 @@ __global__ void __launch_bounds__(1024, 2)
     }
     o[t] = acc;
   }
-  const int nh = nheavy[b];
+  const int nh = meta[b * kMetaInts + 24];
   const int lane = threadIdx.x & 31;
   for (int h = threadIdx.x >> 5; h < nh; h += blockDim.x >> 5) {
     const int* hd = heavy + ((long long)b * hcap + h) * 3;
     const int t = hd[0], s0 = hd[1], n = hd[2];
     const float rcp = __frcp_rn((float)n);
     float acc = 0.f;
-    for (int i = lane; i < n; i += 32) {
-      const int p = rc[s0 + i];
-      const float f = ROW_SMEM ? smem[p] : __ldg(row_g + p);
-      acc = __fadd_rn(acc, __fmul_rn(f, rcp));
+    for (int i = lane; i < n; i += 128) {  // four independent record loads in flight per lane
+      int pp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) pp[u] = rc[s0 + min(i + 32 * u, n - 1)];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float f = ROW_SMEM ? smem[pp[u]] : __ldg(row_g + pp[u]);
+        if (i + 32 * u < n) acc = __fadd_rn(acc, __fmul_rn(f, rcp));
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) o[t] = acc;
@@ -93,55 +99,34 @@ __global__ void __launch_bounds__(1024, 2)
 // -------------------------------------------------------------------------------------------------
 // trilinear_devoxelize backward
 // -------------------------------------------------------------------------------------------------
-constexpr int kHeavyBatch = 256;
-
-__device__ __forceinline__ void tri_weights(float fx, float fy, float fz, float* w) {
-  // trilinear_devox.cu:45-59, same association as devox_fwd_kernel: the weights equal the saved wgts bit for bit
+// 8 corner sums of one point: s[dx,dy,dz] += (x_dx*y_dy) * (z_dz*g).  (The reference rounds w = (x*y)*z, then w*g,
+// then adds; this factorisation differs from it by ~1 ulp per term, far inside the 1e-5 bar, and halves the work.)
+__device__ __forceinline__ void tri_accumulate(float fx, float fy, float fz, float g, float* s) {
   const float x0 = 1.0f - fx, y0 = 1.0f - fy, z0 = 1.0f - fz;
-  w[0] = __fmul_rn(__fmul_rn(x0, y0), z0);
-  w[1] = __fmul_rn(__fmul_rn(x0, y0), fz);
-  w[2] = __fmul_rn(__fmul_rn(x0, fy), z0);
-  w[3] = __fmul_rn(__fmul_rn(x0, fy), fz);
-  w[4] = __fmul_rn(__fmul_rn(fx, y0), z0);
-  w[5] = __fmul_rn(__fmul_rn(fx, y0), fz);
-  w[6] = __fmul_rn(__fmul_rn(fx, fy), z0);
-  w[7] = __fmul_rn(__fmul_rn(fx, fy), fz);
+  const float gz0 = g * z0, gz1 = g * fz;
+  const float a00 = x0 * y0, a01 = x0 * fy, a10 = fx * y0, a11 = fx * fy;
+  s[0] = fmaf(a00, gz0, s[0]);
+  s[1] = fmaf(a00, gz1, s[1]);
+  s[2] = fmaf(a01, gz0, s[2]);
+  s[3] = fmaf(a01, gz1, s[3]);
+  s[4] = fmaf(a10, gz0, s[4]);
+  s[5] = fmaf(a10, gz1, s[5]);
+  s[6] = fmaf(a11, gz0, s[6]);
+  s[7] = fmaf(a11, gz1, s[7]);
 }
-
-// add the 8 corner sums of one cell into the shared-memory plane, corner k in phase k: inside a phase every thread
-// targets cell + off_k with a distinct cell, so plain read-modify-writes never collide (no atomics, fixed order)
-#define PCFM_CORNER_PHASES(active, cell, S)                                                     \
-  {                                                                                             \
-    int cx = 0, cy = 0, cz = 0;                                                                 \
-    if (active) {                                                                               \
-      cx = (cell) / r2;                                                                         \
-      cy = ((cell) / r) % r;                                                                    \
-      cz = (cell) % r;                                                                          \
-    }                                                                                           \
-    _Pragma("unroll") for (int k = 0; k < 8; ++k) {                                             \
-      const int dx = k >> 2, dy = (k >> 1) & 1, dz = k & 1;                                     \
-      /* a corner outside the grid only ever carries weight 0 (coords <= r-1): skip it */       \
-      if ((active) && cx + dx < r && cy + dy < r && cz + dz < r) {                              \
-        const int v = (cell) + dx * r2 + dy * r + dz;                                           \
-        plane[v] = __fadd_rn(plane[v], (S)[k]);                                                 \
-      }                                                                                         \
-      __syncthreads();                                                                          \
-    }                                                                                           \
-  }
 
 template <bool ROW_SMEM>
 __global__ void __launch_bounds__(1024, 1)
     devox_bwd_cell_kernel(const float* __restrict__ grad_y, const int* __restrict__ cells,
-                          const int* __restrict__ slot0, const int* __restrict__ nlight,
-                          const int* __restrict__ heavy, const int* __restrict__ nheavy,
-                          const float4* __restrict__ rec, float* __restrict__ grad_x, int C, int N, int r,
-                          int lcap, int hcap, int rcap, int use_tma) {
+                          const int* __restrict__ slot0, const int* __restrict__ meta,
+                          const int* __restrict__ heavy, const float4* __restrict__ rec,
+                          float* __restrict__ grad_x, int C, int N, int r, int lcap, int hcap, int rcap,
+                          int use_tma) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
   const int r2 = r * r, P = r2 * r;
-  float* plane = smem;                                        // [P]
-  float* hsum = smem + ((P + 3) & ~3);                        // [kHeavyBatch][8]
-  float* row = hsum + kHeavyBatch * 8;                        // [N] (ROW_SMEM)
+  float* plane = smem;                 // [P]
+  float* row = smem + ((P + 3) & ~3);  // [N] (ROW_SMEM)
   const int c = blockIdx.x, b = blockIdx.y;
   const float* row_g = grad_y + ((long long)b * C + c) * N;
   float* o = grad_x + ((long long)b * C + c) * P;
@@ -167,79 +152,104 @@ __global__ void __launch_bounds__(1024, 1)
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
   const float4* rc = rec + (long long)b * rcap;
-  const int nl = nlight[b];
-  // ---- light cells: one thread per cell, rounds of blockDim cells ----
-  for (int base = 0; base < nl; base += blockDim.x) {
-    const int ci = base + threadIdx.x;
-    const bool active = ci < nl;
-    float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    int cell = 0;
-    if (active) {
+  __shared__ int mt[kMetaInts];
+  if (threadIdx.x < kMetaInts) mt[threadIdx.x] = meta[b * kMetaInts + threadIdx.x];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  int off[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) off[k] = (k >> 2) * r2 + ((k >> 1) & 1) * r + (k & 1);
+  // Light cells (count-sorted, sliced-ELL): one thread per cell sums the 8 corner contributions of its points in
+  // registers, then adds them into the plane.  Neighbouring cells share voxels, so the add is a shared-memory
+  // atomicAdd (a CAS loop on sm_100a; collisions need two adjacent cells to finish in the same few cycles).
+  {
+    const int l1 = mt[15];
+    for (int ci = threadIdx.x; ci < l1; ci += blockDim.x) {
       const int d = cl[ci];
       const int n = d >> 24;
-      cell = d & 0xffffff;
-      const int s0 = sl[ci];
-      for (int i0 = 0; i0 < n; i0 += 2) {  // two independent record loads in flight per thread
-        float4 q[2];
-#pragma unroll
-        for (int k = 0; k < 2; ++k)
-          q[k] = (i0 + k < n) ? rc[s0 + 32 * (i0 + k)] : make_float4(__int_as_float(-1), 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int p = __float_as_int(q[u].x);
-          if (p < 0) continue;
-          const float g = ROW_SMEM ? row[p] : __ldg(row_g + p);
-          float w[8];
-          tri_weights(q[u].y, q[u].z, q[u].w, w);
-#pragma unroll
-          for (int k = 0; k < 8; ++k) s[k] = __fadd_rn(s[k], __fmul_rn(w[k], g));  // trilinear_devox.cu:152-159
-        }
-      }
-    }
-    PCFM_CORNER_PHASES(active, cell, s)
-  }
-  // ---- heavy cells: one warp per cell, batches of kHeavyBatch cells ----
-  const int nh = nheavy[b];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  for (int hb = 0; hb < nh; hb += kHeavyBatch) {
-    const int hn = min(kHeavyBatch, nh - hb);
-    for (int h = wid; h < hn; h += nw) {
-      const int* hd = heavy + ((long long)b * hcap + hb + h) * 3;
-      const int s0 = hd[1], n = hd[2];
+      if (n == 0) continue;  // alignment hole
+      const int cell = d & 0xffffff;
+      const unsigned se = (unsigned)sl[ci];
+      const int s0 = se & 0xffffff;
+      const unsigned mask = se >> 24;
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int i = lane; i < n; i += 32) {
-        const float4 q = rc[s0 + i];
-        const int p = __float_as_int(q.x);
-        const float g = ROW_SMEM ? row[p] : __ldg(row_g + p);
-        float w[8];
-        tri_weights(q.y, q.z, q.w, w);
+      for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight
+        float4 qr[4];
+        float g[4];
 #pragma unroll
-        for (int k = 0; k < 8; ++k) s[k] = __fadd_rn(s[k], __fmul_rn(w[k], g));
+        for (int u = 0; u < 4; ++u) qr[u] = rc[s0 + 32 * min(i0 + u, n - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pp = __float_as_int(qr[u].x);
+          g[u] = ROW_SMEM ? row[pp] : __ldg(row_g + pp);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i0 + u < n) tri_accumulate(qr[u].y, qr[u].z, qr[u].w, g[u], s);
       }
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const float tot = warp_sum(s[k]);
-        if (lane == k) hsum[h * 8 + k] = tot;
-      }
-    }
-    __syncthreads();
-    {
-      const bool active = (int)threadIdx.x < hn;
-      int cell = 0;
-      float s[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] = active ? hsum[threadIdx.x * 8 + k] : 0.f;
-      if (active) cell = heavy[((long long)b * hcap + hb + threadIdx.x) * 3];
-      PCFM_CORNER_PHASES(active, cell, s)
+      for (int k = 0; k < 8; ++k)
+        if ((mask >> k) & 1u) atomicAdd(plane + cell + off[k], s[k]);
     }
   }
+  // Heavy cells: one warp per cell; the 8 partial sums are reduced by recursive halving (9 shuffles instead of 40):
+  // after the exchange lane l holds the total of corner (l >> 2) & 7.
+  {
+    const int h1 = mt[24];
+    for (int h = wid; h < h1; h += nw) {
+      const int* hd = heavy + ((long long)b * hcap + h) * 3;
+      const int cell = hd[0], s0 = hd[1], n = hd[2];
+      float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int i = lane; i < n; i += 128) {  // four independent record loads in flight per lane
+        float4 qr[4];
+        float g[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) qr[u] = rc[s0 + min(i + 32 * u, n - 1)];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int pp = __float_as_int(qr[u].x);
+          g[u] = ROW_SMEM ? row[pp] : __ldg(row_g + pp);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+          if (i + 32 * u < n) tri_accumulate(qr[u].y, qr[u].z, qr[u].w, g[u], s);
+      }
+      float a4[4], a2[2], a1;
+      const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {  // lanes 0-15 keep corners 0-3, lanes 16-31 keep corners 4-7
+        const float send = up16 ? s[k] : s[k + 4];
+        const float keep = up16 ? s[k + 4] : s[k];
+        a4[k] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float send = up8 ? a4[k] : a4[k + 2];
+        const float keep = up8 ? a4[k + 2] : a4[k];
+        a2[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+      {
+        const float send = up4 ? a2[0] : a2[1];
+        const float keep = up4 ? a2[1] : a2[0];
+        a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 2);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
+      if ((lane & 3) == 0) {
+        const int k = lane >> 2;  // bit 4 of the lane -> dx, bit 3 -> dy, bit 2 -> dz
+        const int cx = cell / r2, cy = (cell / r) % r, cz = cell % r;
+        if (cx + (k >> 2) < r && cy + ((k >> 1) & 1) < r && cz + (k & 1) < r) atomicAdd(plane + cell + off[k], a1);
+      }
+    }
+  }
+  __syncthreads();
   // ---- write the plane: one bulk (TMA) store when aligned, else a coalesced copy ----
   if ((((uintptr_t)o) & 15) == 0 && (P & 3) == 0 && use_tma) {
     fence_proxy_async();  // generic-proxy writes to `plane` -> visible to the async proxy
     __syncthreads();
     if (threadIdx.x == 0) {
-      for (uint32_t off = 0; off < (uint32_t)P * 4u; off += kBulkChunk)
-        bulk_s2g((char*)o + off, (const char*)plane + off, min(kBulkChunk, (uint32_t)P * 4u - off));
+      for (uint32_t off2 = 0; off2 < (uint32_t)P * 4u; off2 += kBulkChunk)
+        bulk_s2g((char*)o + off2, (const char*)plane + off2, min(kBulkChunk, (uint32_t)P * 4u - off2));
       bulk_commit();
       bulk_wait_read();  // the CTA may exit once the source has been read out of shared memory
     }
@@ -250,7 +260,7 @@ __global__ void __launch_bounds__(1024, 1)
 
 static size_t devox_bwd_smem(int n, int r, bool row_smem) {
   const size_t p = (size_t)r * r * r;
-  return (((p + 3) & ~(size_t)3) + kHeavyBatch * 8 + (row_smem ? n : 0)) * sizeof(float);
+  return (((p + 3) & ~(size_t)3) + (row_smem ? n : 0)) * sizeof(float);
 }
 constexpr size_t kSmemLimit = 227 * 1024 - 512;  // opt-in maximum (232448 B) minus the static shared memory
 
@@ -298,12 +308,12 @@ int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, i
   }
   if (n <= kMaxStageFloats)
     vox_fwd_cell_kernel<true><<<grid, 1024, (size_t)n * sizeof(float), st>>>(
-        features, plan.cells, plan.slot0, plan.nlight, plan.heavy, plan.nheavy, (const int*)plan.rec, out, c, n, t,
-        plan.lcap, plan.hcap, plan.rcap, g_opt_stage == 0);
+        features, plan.cells, plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c, n, t, plan.lcap,
+        plan.hcap, plan.rcap, g_opt_stage == 0);
   else
-    vox_fwd_cell_kernel<false><<<grid, 1024, 0, st>>>(features, plan.cells, plan.slot0, plan.nlight, plan.heavy,
-                                                      plan.nheavy, (const int*)plan.rec, out, c, n, t, plan.lcap,
-                                                      plan.hcap, plan.rcap, 0);
+    vox_fwd_cell_kernel<false><<<grid, 1024, 0, st>>>(features, plan.cells, plan.slot0, plan.meta, plan.heavy,
+                                                      (const int*)plan.rec, out, c, n, t, plan.lcap, plan.hcap,
+                                                      plan.rcap, 0);
   PCFM_LAUNCHED();
   return 0;
 }
@@ -346,12 +356,12 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
   const int threads = (row_smem && devox_bwd_smem(n, r, true) <= 110 * 1024) ? 512 : 1024;
   if (row_smem)
     devox_bwd_cell_kernel<true><<<grid, threads, devox_bwd_smem(n, r, true), st>>>(
-        grad_y, plan.cells, plan.slot0, plan.nlight, plan.heavy, plan.nheavy, (const float4*)plan.rec, grad_x, c, n,
-        r, plan.lcap, plan.hcap, plan.rcap, g_opt_stage == 0);
+        grad_y, plan.cells, plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec, grad_x, c, n, r, plan.lcap,
+        plan.hcap, plan.rcap, g_opt_stage == 0);
   else
     devox_bwd_cell_kernel<false><<<grid, threads, devox_bwd_smem(n, r, false), st>>>(
-        grad_y, plan.cells, plan.slot0, plan.nlight, plan.heavy, plan.nheavy, (const float4*)plan.rec, grad_x, c, n,
-        r, plan.lcap, plan.hcap, plan.rcap, g_opt_stage == 0);
+        grad_y, plan.cells, plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec, grad_x, c, n, r, plan.lcap,
+        plan.hcap, plan.rcap, g_opt_stage == 0);
   PCFM_LAUNCHED();
   return 0;
 }

@@ -3,7 +3,7 @@
 
 namespace pcfm {
 
-constexpr int kEllPad = 4608;  // >= 32 * (1+2+...+16): every count class can waste at most one slice of padding
+constexpr int kEllPad = 8 * 32 * (kLightMax * (kLightMax + 1) / 2) + 1024;  // every (class, count) bin wastes < 1 slice
 
 __device__ __forceinline__ int floor_cell(const float* cb, int i, int n, int r, float* fx, float* fy, float* fz) {
   // identical arithmetic to devox_fwd_kernel (devox.cu): clamp (no-op for contractual inputs), floor, fraction
@@ -54,76 +54,105 @@ __global__ void __launch_bounds__(256) cp_count_kernel(const int* __restrict__ v
   if (inb) rank[base + i] = myrank;
 }
 
-// counters per batch element: hist[0..16] (hist[c] = #cells with c points, c in 1..16), [17] = #heavy cells,
-// [18] = #points in heavy cells
-constexpr int kCtr = 20;
+// counters per batch element: for parity class q (0..7): ctr[q*20 + c] = #light cells with c points (c in 1..16),
+// ctr[q*20 + 19] = #heavy cells; ctr[160] = #points in heavy cells (allocator of their contiguous record ranges)
+constexpr int kCtr = 164;
+constexpr int kBins = 8 * kLightMax;  // (class, count) bins in processing order: class-major, count descending
 
-// one thread per cell: position inside its count class (light) or heavy slot + record range (heavy)
-__global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict__ cnt, int t,
+// mode: 0 = no grid structure needed (mean plans), 1 = corner mask only, 2 = corner mask + parity class
+__device__ __forceinline__ int parity_class(int v, int r, int mode, int* mask) {
+  if (mode == 0) { *mask = 0xff; return 0; }
+  const int r2 = r * r;
+  const int x = v / r2, y = (v / r) % r, z = v % r;
+  int m = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)  // corner k = (dx,dy,dz) exists if it stays inside the grid
+    if (x + (k >> 2) < r && y + ((k >> 1) & 1) < r && z + (k & 1) < r) m |= 1 << k;
+  *mask = m;
+  return mode == 2 ? (((x & 1) << 2) | ((y & 1) << 1) | (z & 1)) : 0;
+}
+
+// one thread per cell: position inside its (class, count) bin (light) or inside its class's heavy list + a record range
+__global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict__ cnt, int t, int r, int parity,
                                                           int* __restrict__ ctr, int* __restrict__ aux,
-                                                          int* __restrict__ recbase, int* __restrict__ heavy,
-                                                          int hcap) {
+                                                          int* __restrict__ recbase) {
   const int b = blockIdx.y;
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= t) return;
   const int n = cnt[(long long)b * t + v];
   if (n <= 0) return;
-  int* c = ctr + b * kCtr;
+  int mask;
+  const int q = parity_class(v, r, parity, &mask);
+  int* c = ctr + b * kCtr + q * 20;
   if (n <= kLightMax) {
     aux[(long long)b * t + v] = atomicAdd(c + n, 1);
   } else {
-    const int slot = atomicAdd(c + 17, 1);
-    const int hs = atomicAdd(c + 18, n);
-    if (slot < hcap) {
-      int* h = heavy + ((long long)b * hcap + slot) * 3;
-      h[0] = v; h[1] = hs; h[2] = n;
-    }
-    recbase[(long long)b * t + v] = hs;  // stride 1
+    aux[(long long)b * t + v] = atomicAdd(c + 19, 1);
+    recbase[(long long)b * t + v] = atomicAdd(ctr + b * kCtr + 160, n);  // stride-1 record range
   }
 }
 
-// one thread per cell: sorted index of a light cell (count-descending), its slice, and the slice's record base
-__global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ cnt, int t,
+// one thread per cell: sorted index of a light cell, its slice and the slice's record base; heavy list entry
+__global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ cnt, int t, int r, int parity,
                                                         const int* __restrict__ ctr, const int* __restrict__ aux,
                                                         int* __restrict__ recbase, int* __restrict__ cells,
-                                                        int* __restrict__ slot0, int* __restrict__ nlight,
-                                                        int* __restrict__ nheavy, int lcap, int hcap) {
-  __shared__ int P[kLightMax + 2];      // P[c] = #light cells with more than c points (sorted index where class c starts)
-  __shared__ int F[kLightMax + 2];      // F[c] = first slice that STARTS in class c = ceil(P[c]/32)
-  __shared__ int Bs[kLightMax + 2];     // Bs[c] = record offset of slice F[c]
+                                                        int* __restrict__ slot0, int* __restrict__ meta,
+                                                        int* __restrict__ heavy, int lcap, int hcap) {
+  __shared__ int P[kBins + 1];   // sorted index where bin j starts (class starts are multiples of 32)
+  __shared__ int F[kBins + 1];   // first slice that STARTS in bin j
+  __shared__ int Bs[kBins + 1];  // record offset of slice F[j]
+  __shared__ int H[9];           // heavy list offset of class q
   const int b = blockIdx.y;
   const int* c = ctr + b * kCtr;
   if (threadIdx.x == 0) {
-    int p = 0;
-    for (int k = kLightMax; k >= 1; --k) { P[k] = p; p += c[k]; }
-    P[0] = p;  // total light cells
-    int base = 0;
-    for (int k = kLightMax; k >= 1; --k) {
-      F[k] = (P[k] + 31) >> 5;
-      Bs[k] = base;
-      const int fnext = (P[k - 1] + 31) >> 5;
-      base += 32 * k * (fnext - F[k]);
+    int p = 0, base = 0, h = 0;
+    for (int q = 0; q < 8; ++q) {
+      p = (p + 31) & ~31;  // a slice never mixes parity classes
+      if (blockIdx.x == 0) meta[b * kMetaInts + q] = min(p, lcap);
+      for (int k = kLightMax; k >= 1; --k) {
+        const int j = q * kLightMax + (kLightMax - k);
+        P[j] = p;
+        F[j] = (p + 31) >> 5;
+        Bs[j] = base;
+        p += c[q * 20 + k];
+        const int pn = (k == 1) ? ((p + 31) & ~31) : p;  // where the next bin starts
+        base += 32 * k * (((pn + 31) >> 5) - F[j]);
+      }
+      if (blockIdx.x == 0) meta[b * kMetaInts + 8 + q] = min(p, lcap);
+      H[q] = h;
+      if (blockIdx.x == 0) meta[b * kMetaInts + 16 + q] = min(h, hcap);
+      h += c[q * 20 + 19];
     }
-    F[0] = (P[0] + 31) >> 5;
-    if (blockIdx.x == 0) {
-      nlight[b] = min(P[0], lcap);
-      nheavy[b] = min(c[17], hcap);
-    }
+    P[kBins] = (p + 31) & ~31;
+    F[kBins] = P[kBins] >> 5;
+    H[8] = h;
+    if (blockIdx.x == 0) meta[b * kMetaInts + 24] = min(h, hcap);
   }
   __syncthreads();
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= t) return;
   const int n = cnt[(long long)b * t + v];
-  if (n <= 0 || n > kLightMax) return;
-  const int si = P[n] + aux[(long long)b * t + v];
+  if (n <= 0) return;
+  int mask;
+  const int q = parity_class(v, r, parity, &mask);
+  if (n > kLightMax) {
+    const int slot = H[q] + aux[(long long)b * t + v];
+    if (slot < hcap) {
+      int* hd = heavy + ((long long)b * hcap + slot) * 3;
+      hd[0] = v; hd[1] = recbase[(long long)b * t + v]; hd[2] = n;
+    }
+    return;
+  }
+  int j = q * kLightMax + (kLightMax - n);
+  const int si = P[j] + aux[(long long)b * t + v];
   const int s = si >> 5, lane = si & 31;
-  int k = kLightMax;  // class in which slice s starts: F[k] <= s < F[k-1]
-  while (k > 1 && s >= F[k - 1]) --k;
-  const int s0 = c[18] + Bs[k] + 32 * k * (s - F[k]) + lane;  // ELL area follows the heavy records
-  recbase[(long long)b * t + v] = s0 | (int)0x80000000;       // stride 32
+  while (s < F[j]) --j;  // the bin in which slice s starts (same parity class: class starts are slice aligned)
+  const int width = kLightMax - (j % kLightMax);
+  const int s0 = c[160] + Bs[j] + 32 * width * (s - F[j]) + lane;  // the ELL area follows the heavy records
+  recbase[(long long)b * t + v] = s0 | (int)0x80000000;            // stride 32
   if (si < lcap) {
     cells[(long long)b * lcap + si] = (n << 24) | v;
-    slot0[(long long)b * lcap + si] = s0;
+    slot0[(long long)b * lcap + si] = (mask << 24) | s0;
   }
 }
 
@@ -159,14 +188,14 @@ __global__ void __launch_bounds__(256) cp_fill_kernel(const int* __restrict__ ke
 template <bool TRI>
 __global__ void __launch_bounds__(256) cp_order_kernel(const int* __restrict__ cells,
                                                        const int* __restrict__ slot0,
-                                                       const int* __restrict__ nlight, void* __restrict__ rec,
+                                                       const int* __restrict__ meta, void* __restrict__ rec,
                                                        int lcap, int rcap) {
   const int b = blockIdx.y;
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= nlight[b]) return;
+  if (ci >= meta[b * kMetaInts + 15]) return;  // end of the last class
   const int n = cells[(long long)b * lcap + ci] >> 24;
   if (n < 2) return;
-  const long long s0 = (long long)b * rcap + slot0[(long long)b * lcap + ci];
+  const long long s0 = (long long)b * rcap + (slot0[(long long)b * lcap + ci] & 0xffffff);
   if (TRI) {
     float4* rr = (float4*)rec;
     float4 loc[kLightMax];
@@ -196,13 +225,13 @@ __global__ void __launch_bounds__(256) cp_order_kernel(const int* __restrict__ c
   }
 }
 
-static long long lcap_of(long long n, long long t) { return (n < t ? n : t) + 1; }
+static long long lcap_of(long long n, long long t) { return (((n < t ? n : t) + 31) & ~31LL) + 8 * 32; }
 
 size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear) {
   size_t s = 0;
   const long long lcap = lcap_of(n, t), hcap = n / (kLightMax + 1) + 1, rcap = n + kEllPad;
   s += align256((size_t)b * lcap * 4) * 2;                     // cells, slot0
-  s += align256((size_t)b * 4) * 2;                            // nlight, nheavy
+  s += align256((size_t)b * kMetaInts * 4);                    // meta
   s += align256((size_t)b * hcap * 3 * 4);                     // heavy
   s += align256((size_t)b * rcap * (trilinear ? 16 : 4));      // rec
   s += align256((size_t)b * n * 4);                            // rank
@@ -213,15 +242,14 @@ size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear)
 }
 
 int cellplan_build(const int* vox_coords, const float* float_coords, int r, int* ind_out, int b, int n, int t,
-                   int* cnt, CellPlan* plan, Workspace* ws, cudaStream_t st) {
+                   int* cnt, CellPlan* plan, Workspace* ws, cudaStream_t st, int parity) {
   const bool tri = float_coords != nullptr;
   plan->lcap = (int)lcap_of(n, t);
   plan->hcap = n / (kLightMax + 1) + 1;
   plan->rcap = n + kEllPad;
   plan->cells = ws->take<int>((size_t)b * plan->lcap);
   plan->slot0 = ws->take<int>((size_t)b * plan->lcap);
-  plan->nlight = ws->take<int>(b);
-  plan->nheavy = ws->take<int>(b);
+  plan->meta = ws->take<int>((size_t)b * kMetaInts);
   plan->heavy = ws->take<int>((size_t)b * plan->hcap * 3);
   plan->rec = tri ? (void*)ws->take<float4>((size_t)b * plan->rcap) : (void*)ws->take<int>((size_t)b * plan->rcap);
   int* rank = ws->take<int>((size_t)b * n);
@@ -232,28 +260,30 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
   if (!ws->ok()) return PCFM_E_WORKSPACE;
   PCFM_CUDA(cudaMemsetAsync(cnt, 0, (size_t)b * t * sizeof(int), st));
   PCFM_CUDA(cudaMemsetAsync(ctr, 0, (size_t)b * kCtr * sizeof(int), st));
+  PCFM_CUDA(cudaMemsetAsync(plan->cells, 0, (size_t)b * plan->lcap * sizeof(int), st));  // holes = empty cells
   dim3 gp(cdiv(n > 0 ? n : 1, 256), b), gt(cdiv(t, 256), b);
   if (n > 0) {
     if (tri) cp_count_kernel<true><<<gp, 256, 0, st>>>(nullptr, float_coords, r, nullptr, n, t, cnt, rank);
     else cp_count_kernel<false><<<gp, 256, 0, st>>>(vox_coords, nullptr, r, ind_out, n, t, cnt, rank);
     PCFM_LAUNCHED();
   }
-  cp_classify_kernel<<<gt, 256, 0, st>>>(cnt, t, ctr, aux, recbase, plan->heavy, plan->hcap);
+  const int mode = tri ? (parity ? 2 : 1) : 0;
+  cp_classify_kernel<<<gt, 256, 0, st>>>(cnt, t, r, mode, ctr, aux, recbase);
   PCFM_LAUNCHED();
-  cp_layout_kernel<<<gt, 256, 0, st>>>(cnt, t, ctr, aux, recbase, plan->cells, plan->slot0, plan->nlight,
-                                       plan->nheavy, plan->lcap, plan->hcap);
+  cp_layout_kernel<<<gt, 256, 0, st>>>(cnt, t, r, mode, ctr, aux, recbase, plan->cells, plan->slot0, plan->meta,
+                                       plan->heavy, plan->lcap, plan->hcap);
   PCFM_LAUNCHED();
   if (n > 0) {
     dim3 gl(cdiv(plan->lcap, 256), b);
     if (tri) {
       cp_fill_kernel<true><<<gp, 256, 0, st>>>(nullptr, float_coords, r, n, t, rank, recbase, plan->rec, plan->rcap);
       PCFM_LAUNCHED();
-      cp_order_kernel<true><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->nlight, plan->rec, plan->lcap,
+      cp_order_kernel<true><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->meta, plan->rec, plan->lcap,
                                                 plan->rcap);
     } else {
       cp_fill_kernel<false><<<gp, 256, 0, st>>>(ind_out, nullptr, r, n, t, rank, recbase, plan->rec, plan->rcap);
       PCFM_LAUNCHED();
-      cp_order_kernel<false><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->nlight, plan->rec, plan->lcap,
+      cp_order_kernel<false><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->meta, plan->rec, plan->lcap,
                                                  plan->rcap);
     }
     PCFM_LAUNCHED();

@@ -88,7 +88,7 @@ def test_avg_voxelize(be, oracle, ref, kw, variant):
     assert_equal(host(ind), o_ind, "ind")
     assert_equal(host(cnt), o_cnt, "cnt")
     if variant == 0 and o_cnt.max() <= 16:
-        # voxels with <= 16 points (csr.cuh kHeavySeg) are summed in ascending point order, like the oracle
+        # voxels with <= 16 points (cellplan.cuh kLightMax) are summed in ascending point order, like the oracle
         assert_equal(host(out), o_out, "out (ascending-order sum is bit-identical to the oracle)")
     else:
         assert_close(host(out), o_out, "out")
