@@ -81,15 +81,10 @@ __global__ void __launch_bounds__(1024, 2)
     const int t = hd[0], s0 = hd[1], n = hd[2];
     const float rcp = __frcp_rn((float)n);
     float acc = 0.f;
-    for (int i = lane; i < n; i += 128) {  // four independent record loads in flight per lane
-      int pp[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) pp[u] = rc[s0 + min(i + 32 * u, n - 1)];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float f = ROW_SMEM ? smem[pp[u]] : __ldg(row_g + pp[u]);
-        if (i + 32 * u < n) acc = __fadd_rn(acc, __fmul_rn(f, rcp));
-      }
+    for (int i = lane; i < n; i += 32) {
+      const int p = rc[s0 + i];
+      const float f = ROW_SMEM ? smem[p] : __ldg(row_g + p);
+      acc = __fadd_rn(acc, __fmul_rn(f, rcp));
     }
     acc = warp_sum(acc);
     if (lane == 0) o[t] = acc;
@@ -200,19 +195,11 @@ __global__ void __launch_bounds__(1024, 1)
       const int* hd = heavy + ((long long)b * hcap + h) * 3;
       const int cell = hd[0], s0 = hd[1], n = hd[2];
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int i = lane; i < n; i += 128) {  // four independent record loads in flight per lane
-        float4 qr[4];
-        float g[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) qr[u] = rc[s0 + min(i + 32 * u, n - 1)];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int pp = __float_as_int(qr[u].x);
-          g[u] = ROW_SMEM ? row[pp] : __ldg(row_g + pp);
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (i + 32 * u < n) tri_accumulate(qr[u].y, qr[u].z, qr[u].w, g[u], s);
+      for (int i = lane; i < n; i += 32) {
+        const float4 q0 = rc[s0 + i];
+        const int p0 = __float_as_int(q0.x);
+        const float g0 = ROW_SMEM ? row[p0] : __ldg(row_g + p0);
+        tri_accumulate(q0.y, q0.z, q0.w, g0, s);
       }
       float a4[4], a2[2], a1;
       const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;

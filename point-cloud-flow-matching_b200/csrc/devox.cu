@@ -67,11 +67,26 @@ __global__ void __launch_bounds__(1024, 1)
   int* ib = inds ? inds + (long long)b * 8 * n : nullptr;
   float* wb = wgts ? wgts + (long long)b * 8 * n : nullptr;
   const float hi = (float)(r - 1);
+  // software pipeline: the coordinates of the next point are requested before the current one is gathered
+  float nx = 0.f, ny = 0.f, nz = 0.f;
+  if ((int)threadIdx.x < n) {
+    nx = cb[threadIdx.x];
+    ny = cb[(long long)threadIdx.x + n];
+    nz = cb[(long long)threadIdx.x + 2LL * n];
+  }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     // coords are contractually in [0, r-1]; the clamp is a no-op there and keeps every index in range otherwise
-    const float x = fminf(fmaxf(cb[i], 0.f), hi);
-    const float y = fminf(fmaxf(cb[(long long)i + n], 0.f), hi);
-    const float z = fminf(fmaxf(cb[(long long)i + 2LL * n], 0.f), hi);
+    const float x = fminf(fmaxf(nx, 0.f), hi);
+    const float y = fminf(fmaxf(ny, 0.f), hi);
+    const float z = fminf(fmaxf(nz, 0.f), hi);
+    {
+      const int inext = i + blockDim.x;
+      if (inext < n) {
+        nx = cb[inext];
+        ny = cb[(long long)inext + n];
+        nz = cb[(long long)inext + 2LL * n];
+      }
+    }
     const float xl = floorf(x), yl = floorf(y), zl = floorf(z);
     const float x1 = x - xl, y1 = y - yl, z1 = z - zl;
     const float x0 = 1.0f - x1, y0 = 1.0f - y1, z0 = 1.0f - z1;
