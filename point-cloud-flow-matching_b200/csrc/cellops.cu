@@ -168,19 +168,36 @@ __global__ void __launch_bounds__(1024, 1)
       const int s0 = se & 0xffffff;
       const unsigned mask = se >> 24;
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight
+      // records are walked 4 / 2 / 1 at a time: independent loads in flight, no padded work (slices are count-sorted,
+      // so the lanes of a warp take the same path except at slice boundaries)
+      int i0 = 0;
+      for (; i0 + 4 <= n; i0 += 4) {
         float4 qr[4];
         float g[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) qr[u] = rc[s0 + 32 * min(i0 + u, n - 1)];
+        for (int u = 0; u < 4; ++u) qr[u] = rc[s0 + 32 * (i0 + u)];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const int pp = __float_as_int(qr[u].x);
           g[u] = ROW_SMEM ? row[pp] : __ldg(row_g + pp);
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
-          if (i0 + u < n) tri_accumulate(qr[u].y, qr[u].z, qr[u].w, g[u], s);
+        for (int u = 0; u < 4; ++u) tri_accumulate(qr[u].y, qr[u].z, qr[u].w, g[u], s);
+      }
+      if (i0 + 2 <= n) {
+        const float4 qa = rc[s0 + 32 * i0], qb = rc[s0 + 32 * (i0 + 1)];
+        const int pa = __float_as_int(qa.x), pb = __float_as_int(qb.x);
+        const float ga = ROW_SMEM ? row[pa] : __ldg(row_g + pa);
+        const float gb = ROW_SMEM ? row[pb] : __ldg(row_g + pb);
+        tri_accumulate(qa.y, qa.z, qa.w, ga, s);
+        tri_accumulate(qb.y, qb.z, qb.w, gb, s);
+        i0 += 2;
+      }
+      if (i0 < n) {
+        const float4 qa = rc[s0 + 32 * i0];
+        const int pa = __float_as_int(qa.x);
+        const float ga = ROW_SMEM ? row[pa] : __ldg(row_g + pa);
+        tri_accumulate(qa.y, qa.z, qa.w, ga, s);
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k)
