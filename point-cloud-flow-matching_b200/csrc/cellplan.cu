@@ -54,9 +54,11 @@ __global__ void __launch_bounds__(256) cp_count_kernel(const int* __restrict__ v
   if (inb) rank[base + i] = myrank;
 }
 
-// counters per batch element: for parity class q (0..7): ctr[q*20 + c] = #light cells with c points (c in 1..16),
-// ctr[q*20 + 19] = #heavy cells; ctr[160] = #points in heavy cells (allocator of their contiguous record ranges)
-constexpr int kCtr = 164;
+// counters per batch element: for parity class q (0..7): ctr[q*kCls + c] = #light cells with c points (c in
+// 1..kLightMax), ctr[q*kCls + kLightMax+1] = #heavy cells; ctr[8*kCls] = #points in heavy cells (allocator of their
+// contiguous record ranges)
+constexpr int kCls = kLightMax + 2;            // per-class counter stride: [1..kLightMax] light bins, [kLightMax+1] heavy cells
+constexpr int kCtr = 8 * kCls + 4;             // [8*kCls] = points in heavy cells
 constexpr int kBins = 8 * kLightMax;  // (class, count) bins in processing order: class-major, count descending
 
 // mode: 0 = no grid structure needed (mean plans), 1 = corner mask only, 2 = corner mask + parity class
@@ -83,12 +85,12 @@ __global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict_
   if (n <= 0) return;
   int mask;
   const int q = parity_class(v, r, parity, &mask);
-  int* c = ctr + b * kCtr + q * 20;
+  int* c = ctr + b * kCtr + q * kCls;
   if (n <= kLightMax) {
     aux[(long long)b * t + v] = atomicAdd(c + n, 1);
   } else {
-    aux[(long long)b * t + v] = atomicAdd(c + 19, 1);
-    recbase[(long long)b * t + v] = atomicAdd(ctr + b * kCtr + 160, n);  // stride-1 record range
+    aux[(long long)b * t + v] = atomicAdd(c + kLightMax + 1, 1);
+    recbase[(long long)b * t + v] = atomicAdd(ctr + b * kCtr + 8 * kCls, n);  // stride-1 record range
   }
 }
 
@@ -102,8 +104,10 @@ __global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ 
   __shared__ int F[kBins + 1];   // first slice that STARTS in bin j
   __shared__ int Bs[kBins + 1];  // record offset of slice F[j]
   __shared__ int H[9];           // heavy list offset of class q
+  __shared__ int c[kCtr];
   const int b = blockIdx.y;
-  const int* c = ctr + b * kCtr;
+  for (int i = threadIdx.x; i < kCtr; i += blockDim.x) c[i] = ctr[b * kCtr + i];  // coalesced, not 270 serial reads
+  __syncthreads();
   if (threadIdx.x == 0) {
     int p = 0, base = 0, h = 0;
     for (int q = 0; q < 8; ++q) {
@@ -114,14 +118,14 @@ __global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ 
         P[j] = p;
         F[j] = (p + 31) >> 5;
         Bs[j] = base;
-        p += c[q * 20 + k];
+        p += c[q * kCls + k];
         const int pn = (k == 1) ? ((p + 31) & ~31) : p;  // where the next bin starts
         base += 32 * k * (((pn + 31) >> 5) - F[j]);
       }
       if (blockIdx.x == 0) meta[b * kMetaInts + 8 + q] = min(p, lcap);
       H[q] = h;
       if (blockIdx.x == 0) meta[b * kMetaInts + 16 + q] = min(h, hcap);
-      h += c[q * 20 + 19];
+      h += c[q * kCls + kLightMax + 1];
     }
     P[kBins] = (p + 31) & ~31;
     F[kBins] = P[kBins] >> 5;
@@ -148,7 +152,7 @@ __global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ 
   const int s = si >> 5, lane = si & 31;
   while (s < F[j]) --j;  // the bin in which slice s starts (same parity class: class starts are slice aligned)
   const int width = kLightMax - (j % kLightMax);
-  const int s0 = c[160] + Bs[j] + 32 * width * (s - F[j]) + lane;  // the ELL area follows the heavy records
+  const int s0 = c[8 * kCls] + Bs[j] + 32 * width * (s - F[j]) + lane;  // the ELL area follows the heavy records
   recbase[(long long)b * t + v] = s0 | (int)0x80000000;            // stride 32
   if (si < lcap) {
     cells[(long long)b * lcap + si] = (n << 24) | v;
@@ -194,13 +198,13 @@ __global__ void __launch_bounds__(256) cp_order_kernel(const int* __restrict__ c
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= meta[b * kMetaInts + 15]) return;  // end of the last class
   const int n = cells[(long long)b * lcap + ci] >> 24;
-  if (n < 2) return;
+  if (n < 2 || n > kSortMax) return;
   const long long s0 = (long long)b * rcap + (slot0[(long long)b * lcap + ci] & 0xffffff);
   if (TRI) {
     float4* rr = (float4*)rec;
-    float4 loc[kLightMax];
+    float4 loc[kSortMax];
 #pragma unroll
-    for (int a = 0; a < kLightMax; ++a)
+    for (int a = 0; a < kSortMax; ++a)
       if (a < n) loc[a] = rr[s0 + 32 * a];
     for (int a = 1; a < n; ++a) {
       const float4 x = loc[a];
@@ -211,9 +215,9 @@ __global__ void __launch_bounds__(256) cp_order_kernel(const int* __restrict__ c
     for (int a = 0; a < n; ++a) rr[s0 + 32 * a] = loc[a];
   } else {
     int* rr = (int*)rec;
-    int loc[kLightMax];
+    int loc[kSortMax];
 #pragma unroll
-    for (int a = 0; a < kLightMax; ++a)
+    for (int a = 0; a < kSortMax; ++a)
       if (a < n) loc[a] = rr[s0 + 32 * a];
     for (int a = 1; a < n; ++a) {
       const int x = loc[a];
@@ -230,13 +234,12 @@ static long long lcap_of(long long n, long long t) { return (((n < t ? n : t) + 
 size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear) {
   size_t s = 0;
   const long long lcap = lcap_of(n, t), hcap = n / (kLightMax + 1) + 1, rcap = n + kEllPad;
-  s += align256((size_t)b * lcap * 4) * 2;                     // cells, slot0
+  s += align256((size_t)b * lcap * 4) * 2 + align256((size_t)b * kCtr * 4);  // cells (+counters), slot0
   s += align256((size_t)b * kMetaInts * 4);                    // meta
   s += align256((size_t)b * hcap * 3 * 4);                     // heavy
   s += align256((size_t)b * rcap * (trilinear ? 16 : 4));      // rec
   s += align256((size_t)b * n * 4);                            // rank
   s += align256((size_t)b * t * 4) * 2;                        // aux, recbase
-  s += align256((size_t)b * kCtr * 4);                         // counters
   if (trilinear) s += align256((size_t)b * t * 4);             // cnt (caller has none)
   return s + 256;
 }
@@ -247,7 +250,11 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
   plan->lcap = (int)lcap_of(n, t);
   plan->hcap = n / (kLightMax + 1) + 1;
   plan->rcap = n + kEllPad;
-  plan->cells = ws->take<int>((size_t)b * plan->lcap);
+  // cells and the counters are zeroed by ONE memset: they are carved from one block
+  const size_t zero_ints = (size_t)b * plan->lcap + (size_t)b * kCtr;
+  int* zero_block = ws->take<int>(zero_ints);
+  plan->cells = zero_block;
+  int* ctr = zero_block ? zero_block + (size_t)b * plan->lcap : nullptr;
   plan->slot0 = ws->take<int>((size_t)b * plan->lcap);
   plan->meta = ws->take<int>((size_t)b * kMetaInts);
   plan->heavy = ws->take<int>((size_t)b * plan->hcap * 3);
@@ -255,12 +262,10 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
   int* rank = ws->take<int>((size_t)b * n);
   int* aux = ws->take<int>((size_t)b * t);
   int* recbase = ws->take<int>((size_t)b * t);
-  int* ctr = ws->take<int>((size_t)b * kCtr);
   if (!cnt) cnt = ws->take<int>((size_t)b * t);
   if (!ws->ok()) return PCFM_E_WORKSPACE;
   PCFM_CUDA(cudaMemsetAsync(cnt, 0, (size_t)b * t * sizeof(int), st));
-  PCFM_CUDA(cudaMemsetAsync(ctr, 0, (size_t)b * kCtr * sizeof(int), st));
-  PCFM_CUDA(cudaMemsetAsync(plan->cells, 0, (size_t)b * plan->lcap * sizeof(int), st));  // holes = empty cells
+  PCFM_CUDA(cudaMemsetAsync(zero_block, 0, zero_ints * sizeof(int), st));  // counters; holes in `cells` = empty
   dim3 gp(cdiv(n > 0 ? n : 1, 256), b), gt(cdiv(t, 256), b);
   if (n > 0) {
     if (tri) cp_count_kernel<true><<<gp, 256, 0, st>>>(nullptr, float_coords, r, nullptr, n, t, cnt, rank);

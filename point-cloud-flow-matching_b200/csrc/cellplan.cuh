@@ -13,7 +13,8 @@
 
 namespace pcfm {
 
-constexpr int kLightMax = 16;  // longer cells are reduced by a whole warp
+constexpr int kLightMax = 32;  // longer cells are reduced by a whole warp
+constexpr int kSortMax = 16;   // light cells up to this size keep their records in ascending point order
 
 // Parity classes (trilinear plans): cells are additionally grouped by the parity of (x,y,z).  Two cells of the same
 // class are at least two voxels apart along every axis, so their 2x2x2 corner blocks are disjoint: all cells of one

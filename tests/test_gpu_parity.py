@@ -87,7 +87,7 @@ def test_avg_voxelize(be, oracle, ref, kw, variant):
     o_out, o_ind, o_cnt = oracle.avg_voxelize_forward(feat, host(vox), res)
     assert_equal(host(ind), o_ind, "ind")
     assert_equal(host(cnt), o_cnt, "cnt")
-    if variant == 0 and o_cnt.max() <= 16:
+    if variant == 0 and o_cnt.max() <= 16:  # kSortMax
         # voxels with <= 16 points (cellplan.cuh kLightMax) are summed in ascending point order, like the oracle
         assert_equal(host(out), o_out, "out (ascending-order sum is bit-identical to the oracle)")
     else:
