@@ -137,54 +137,76 @@ constexpr int kApThreads = 128;
 constexpr int kApRows = 16;  // own points per thread => 2048 rows per sweep
 constexpr int kApMaxM = 8192;
 
+// Minima are taken on the IEEE bit patterns with the 3-input integer min (VIMNMX3): squared distances are >= +0,
+// where unsigned order == float order, so two distances are folded per instruction for the row side and two for
+// the column side: 3 FADD + FMUL + 2 FFMA + 1 VIMNMX3 = 7 issue slots per evaluated pair of points.
 __global__ void __launch_bounds__(kApThreads)
     chamfer_allpairs_kernel(const float* __restrict__ s, const float* __restrict__ rr, int nr, int n, int m,
                             float* __restrict__ cd) {
   extern __shared__ __align__(16) unsigned char ap_smem[];
-  float4* col = (float4*)ap_smem;               // [m]
-  unsigned* colmin = (unsigned*)(col + m);      // [m]
+  const int m2 = (m + 1) & ~1;                  // columns are walked two at a time; the pad column sits at +inf
+  float4* col = (float4*)ap_smem;               // [m2]
+  unsigned* colmin = (unsigned*)(col + m2);     // [m2]
   __shared__ float red[kApThreads / 32];
+  __shared__ float red2[kApThreads / 32];
   const long long pair = blockIdx.x;
   const int i = (int)(pair / nr), j = (int)(pair % nr);
   const float* a = s + (long long)i * n * 3;
   const float* o = rr + (long long)j * m * 3;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  for (int k = threadIdx.x; k < m; k += kApThreads) {
-    const float* p = o + (long long)k * 3;
-    col[k] = make_float4(p[0], p[1], p[2], 0.f);
+  for (int k = threadIdx.x; k < m2; k += kApThreads) {
+    if (k < m) {
+      const float* p = o + (long long)k * 3;
+      col[k] = make_float4(p[0], p[1], p[2], 0.f);
+    } else {
+      col[k] = make_float4(pos_inf(), pos_inf(), pos_inf(), 0.f);
+    }
     colmin[k] = 0x7f800000u;
   }
   __syncthreads();
   float rowsum = 0.f;
   for (int base = 0; base < n; base += kApThreads * kApRows) {
-    float ax[kApRows], ay[kApRows], az[kApRows], rmin[kApRows];
+    float ax[kApRows], ay[kApRows], az[kApRows];
+    unsigned rmin[kApRows];
 #pragma unroll
     for (int r = 0; r < kApRows; ++r) {
       const int row = base + r * kApThreads + threadIdx.x;
       const bool v = row < n;
-      // rows past the end sit at +inf: their distances are +inf (or NaN) and never lower a minimum
+      // rows past the end sit at +inf: their distances are +inf (or NaN -> masked below) and never lower a minimum
       ax[r] = v ? a[(long long)row * 3 + 0] : pos_inf();
       ay[r] = v ? a[(long long)row * 3 + 1] : pos_inf();
       az[r] = v ? a[(long long)row * 3 + 2] : pos_inf();
-      rmin[r] = pos_inf();
+      rmin[r] = 0x7f800000u;
     }
-    for (int k = 0; k < m; ++k) {
-      const float4 q = col[k];
-      float cm = pos_inf();
+    for (int k = 0; k < m2; k += 2) {
+      const float4 q0 = col[k], q1 = col[k + 1];
+      unsigned cm0 = 0x7f800000u, cm1 = 0x7f800000u;
 #pragma unroll
-      for (int r = 0; r < kApRows; ++r) {
-        const float d = sq3(q.x - ax[r], q.y - ay[r], q.z - az[r]);
-        rmin[r] = fminf(rmin[r], d);
-        cm = fminf(cm, d);
+      for (int r = 0; r < kApRows; r += 2) {
+        // inf - inf = NaN only when a pad row meets the pad column: fminf(.., inf) maps it back to +inf
+        const unsigned d00 = __float_as_uint(sq3(q0.x - ax[r], q0.y - ay[r], q0.z - az[r]));
+        const unsigned d01 = __float_as_uint(sq3(q1.x - ax[r], q1.y - ay[r], q1.z - az[r]));
+        const unsigned d10 = __float_as_uint(sq3(q0.x - ax[r + 1], q0.y - ay[r + 1], q0.z - az[r + 1]));
+        const unsigned d11 = __float_as_uint(sq3(q1.x - ax[r + 1], q1.y - ay[r + 1], q1.z - az[r + 1]));
+        rmin[r] = __vimin3_u32(rmin[r], d00, d01);
+        rmin[r + 1] = __vimin3_u32(rmin[r + 1], d10, d11);
+        cm0 = __vimin3_u32(cm0, d00, d10);
+        cm1 = __vimin3_u32(cm1, d01, d11);
       }
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) cm = fminf(cm, __shfl_xor_sync(0xffffffffu, cm, off));
-      if (lane == 0) atomicMin(colmin + k, __float_as_uint(cm));
+      for (int off = 16; off > 0; off >>= 1) {
+        cm0 = min(cm0, __shfl_xor_sync(0xffffffffu, cm0, off));
+        cm1 = min(cm1, __shfl_xor_sync(0xffffffffu, cm1, off));
+      }
+      if (lane == 0) {
+        atomicMin(colmin + k, cm0);
+        atomicMin(colmin + k + 1, cm1);
+      }
     }
 #pragma unroll
     for (int r = 0; r < kApRows; ++r) {
       const int row = base + r * kApThreads + threadIdx.x;
-      if (row < n) rowsum += rmin[r];
+      if (row < n) rowsum += __uint_as_float(rmin[r]);
     }
   }
   __syncthreads();
@@ -192,7 +214,6 @@ __global__ void __launch_bounds__(kApThreads)
   for (int k = threadIdx.x; k < m; k += kApThreads) colsum += __uint_as_float(colmin[k]);
   rowsum = warp_sum(rowsum);
   colsum = warp_sum(colsum);
-  __shared__ float red2[kApThreads / 32];
   if (lane == 0) {
     red[wid] = rowsum;
     red2[wid] = colsum;
@@ -266,10 +287,10 @@ int pcfm_chamfer3d_allpairs(const float* s, const float* r, int ns, int nr, int 
   static bool attr_set = false;
   if (!attr_set) {
     PCFM_CUDA(cudaFuncSetAttribute(chamfer_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   kApMaxM * 20));
+                                   (kApMaxM + 2) * 20));
     attr_set = true;
   }
-  const size_t smem = (size_t)m * 20;
+  const size_t smem = (size_t)((m + 1) & ~1) * 20;
   chamfer_allpairs_kernel<<<(unsigned)((long long)ns * nr), kApThreads, smem, (cudaStream_t)stream>>>(
       s, r, nr, n, m, cd);
   PCFM_LAUNCHED();
