@@ -133,8 +133,8 @@ __global__ void __launch_bounds__(256)
 // the float bit pattern per warp; non-negative floats order like unsigned ints).  No indices are needed for
 // the metric, so the inner loop is 3 FADD + FMUL + 2 FFMA + 2 FMNMX per pair of points.
 // =================================================================================================
-constexpr int kApThreads = 128;
-constexpr int kApRows = 16;  // own points per thread => 2048 rows per sweep
+constexpr int kApThreads = 64;
+constexpr int kApRows = 32;  // own points per thread => 2048 rows per sweep
 constexpr int kApMaxM = 8192;
 
 // Minima are taken on the IEEE bit patterns with the 3-input integer min (VIMNMX3): squared distances are >= +0,
