@@ -59,7 +59,7 @@ def algorithmic_bytes(op, c, r, b=B, n=NPTS):
 
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 50 ms from the last warm-up steps to the end of the timed
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms from the last warm-up steps to the end of the timed
     region (the timed region alone is ~0.1 s)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -68,7 +68,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "50"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except OSError:
             self.p = None
@@ -83,7 +83,7 @@ class ClockSampler:
         except subprocess.TimeoutExpired:
             self.p.kill()
         self.f.flush()
-        rows = [ln.strip().split(", ") for ln in open(self.f.name) if ln.strip()]
+        rows = [[c.strip() for c in ln.strip().split(",")] for ln in open(self.f.name) if ln.strip()]
         os.unlink(self.f.name)
         sm, mx, reasons = [], [], set()
         for r in rows:
@@ -226,7 +226,7 @@ def run_ours(args):
     step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    for _ in range(max(args.warmup, 3) + 10):   # >= W warm-up steps, under the clock sampler
+    for _ in range(max(args.warmup, 3) + 60):   # >= W warm-up steps (~0.2 s), under the clock sampler
         step()
     barrier()
     _lib.reset_launch_count()
@@ -283,14 +283,35 @@ def run_ours(args):
     h_out = [torch.empty(B, c, NPTS).pin_memory() for (c, r) in STAGES]
     voxmods = [Voxelization(r, normalize=True, eps=1e-6) for (c, r) in STAGES]
 
+    s_in, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
     def e2e_step():
-        for (c, r), (hf, hc), ho, vm in zip(STAGES, h_in, h_out, voxmods):
-            f = hf.to(dev, non_blocking=True).requires_grad_(True)
-            x = hc.to(dev, non_blocking=True)
+        """Every step copies all inputs host->device and all results device->host.  Three streams: uploads of the next
+        PVConv instance and downloads of the previous one overlap the kernels of the current one (full-duplex PCIe)."""
+        main = torch.cuda.current_stream(dev)
+        staged = []
+        with torch.cuda.stream(s_in):
+            for hf, hc in h_in:
+                f = hf.to(dev, non_blocking=True)
+                x = hc.to(dev, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_in)
+                staged.append((f, x, ev))
+        for (c, r), (f, x, ev), ho, vm in zip(STAGES, staged, h_out, voxmods):
+            main.wait_event(ev)
+            f.record_stream(main)
+            x.record_stream(main)
+            f.requires_grad_(True)
             grid, nc = vm(f, x)
             o = F.trilinear_devoxelize(grid, nc, r, True)
             o.sum().backward()
-            ho.copy_(f.grad, non_blocking=True)
+            g = f.grad
+            done = torch.cuda.Event()
+            done.record(main)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                g.record_stream(s_out)
+                ho.copy_(g, non_blocking=True)
         torch.cuda.synchronize()
 
     e2e_steps = max(3, args.steps // 4)
@@ -306,7 +327,8 @@ def run_ours(args):
     d2h = sum(ho.numel() * 4 for ho in h_out)
     e2e = {"value": pts_per_step / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
-           "api": "pcfm.nn.Voxelization + pcfm.functional.trilinear_devoxelize + autograd backward, pinned host tensors in/out"}
+           "api": "pcfm.nn.Voxelization + pcfm.functional.trilinear_devoxelize + autograd backward; pinned host tensors "
+                  "in and out every step, uploads / kernels / downloads on three streams"}
     del h_in, h_out
 
     # ---------------- all-pairs CD / EMD (config 4 shapes), rows sharded over ranks ----------------

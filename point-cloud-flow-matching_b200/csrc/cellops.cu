@@ -293,7 +293,7 @@ int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, i
                               pcfm_stream_t stream) {
   if (b < 0 || c < 0 || n < 0 || r <= 0 || (long long)r * r * r > (1 << 24)) return PCFM_E_BADARG;
   if (b == 0) return 0;
-  if (!coords || !ind || !cnt || (c > 0 && (!features || !out))) return PCFM_E_BADARG;
+  if (!cnt || (c > 0 && !out) || (n > 0 && (!coords || !ind || (c > 0 && !features)))) return PCFM_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   if (g_opt_vox_fwd != 0)
     return avg_voxelize_forward_generic(features, coords, b, c, n, r, out, ind, cnt, workspace,

@@ -283,8 +283,13 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
     if (tri) {
       cp_fill_kernel<true><<<gp, 256, 0, st>>>(nullptr, float_coords, r, n, t, rank, recbase, plan->rec, plan->rcap);
       PCFM_LAUNCHED();
-      cp_order_kernel<true><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->meta, plan->rec, plan->lcap,
-                                                plan->rcap);
+      // no ordering pass for trilinear plans: their consumer adds cell sums with shared-memory atomics, whose order
+      // is not fixed anyway (the pass costs ~15 us per call; parity != 0 re-enables it for an ordered consumer)
+      if (parity)
+        cp_order_kernel<true><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->meta, plan->rec, plan->lcap,
+                                                  plan->rcap);
+      else
+        --g_launches;
     } else {
       cp_fill_kernel<false><<<gp, 256, 0, st>>>(ind_out, nullptr, r, n, t, rank, recbase, plan->rec, plan->rcap);
       PCFM_LAUNCHED();

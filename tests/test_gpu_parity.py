@@ -442,3 +442,67 @@ def test_inputs_are_not_mutated_and_streams_are_respected(be):
     ref_out = be.pvcnn.avg_voxelize_forward(f, vox, res)[0]
     torch.cuda.synchronize()
     assert torch.allclose(out, ref_out, rtol=1e-5, atol=1e-6) and torch.equal(f, f0) and torch.equal(vox, v0)
+
+
+# ------------------------------------------------------------------------------------------------ edge cases
+def test_empty_and_degenerate_inputs(be, oracle):
+    dev = "cuda"
+    # no points: every voxel empty, devoxelize of nothing
+    out, ind, cnt = be.pvcnn.avg_voxelize_forward(torch.zeros(2, 4, 0, device=dev), torch.zeros(2, 3, 0, dtype=torch.int32, device=dev), 4)
+    assert out.shape == (2, 4, 64) and float(out.abs().sum()) == 0 and int(cnt.sum()) == 0 and ind.shape == (2, 0)
+    o, i, w = be.pvcnn.trilinear_devoxelize_forward(4, True, torch.zeros(2, 3, 0, device=dev), torch.randn(2, 4, 64, device=dev))
+    assert o.shape == (2, 4, 0) and i.shape == (2, 8, 0)
+    g = be.pvcnn.trilinear_devoxelize_backward_coords(torch.zeros(2, 4, 0, device=dev), torch.zeros(2, 3, 0, device=dev), 4)
+    assert g.shape == (2, 4, 64) and float(g.abs().sum()) == 0
+    # empty batch
+    assert be.pvcnn.avg_voxelize_forward(torch.zeros(0, 4, 10, device=dev), torch.zeros(0, 3, 10, dtype=torch.int32, device=dev), 4)[0].shape == (0, 4, 64)
+    # chamfer with an empty second cloud: the reference's loops do not run, outputs keep the caller's zeros, returns 1
+    x = torch.randn(2, 5, 3, device=dev); y = torch.zeros(2, 0, 3, device=dev)
+    d1 = torch.zeros(2, 5, device=dev); d2 = torch.zeros(2, 0, device=dev)
+    i1 = torch.zeros(2, 5, dtype=torch.int32, device=dev); i2 = torch.zeros(2, 0, dtype=torch.int32, device=dev)
+    assert be.chamfer.forward(x, y, d1, d2, i1, i2) == 1 and float(d1.abs().sum()) == 0
+    # ball query over no points / grouping of no centres
+    assert int(be.pvcnn.ball_query(torch.randn(1, 3, 4, device=dev), torch.zeros(1, 3, 0, device=dev), 1.0, 3).sum()) == 0
+    assert be.pvcnn.grouping_forward(torch.randn(1, 2, 9, device=dev), torch.zeros(1, 0, 3, dtype=torch.int32, device=dev)).shape == (1, 2, 0, 3)
+
+
+def test_all_points_in_one_voxel_and_long_rows(be, oracle):
+    """One cell holding every point (a single 'heavy' cell) and rows too long for shared memory (N = 60000)."""
+    r0 = rng(71)
+    n, res = 60000, 4
+    feat = r0.standard_normal((1, 3, n)).astype(np.float32)
+    vox = np.full((1, 3, n), 2, np.int32)
+    vox[0, :, : n // 2] = r0.integers(0, res, size=(3, n // 2))
+    out, ind, cnt = be.pvcnn.avg_voxelize_forward(cu(feat), cu(vox), res)
+    o_out, o_ind, o_cnt = oracle.avg_voxelize_forward(feat, vox, res)
+    assert_equal(host(ind), o_ind, "ind"); assert_equal(host(cnt), o_cnt, "cnt")
+    assert_close(host(out), o_out, "out", atol_frac=1e-5)
+    coords = (r0.random((1, 3, n)) * (res - 1)).astype(np.float32)
+    coords[0, :, ::3] = 1.5
+    gy = r0.standard_normal((1, 3, n)).astype(np.float32)
+    grid = r0.standard_normal((1, 3, res ** 3)).astype(np.float32)
+    outs, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(coords), cu(grid))
+    oo, oi, ow = oracle.trilinear_devoxelize_forward(res, coords, grid)
+    assert_equal(host(inds), oi, "inds"); assert_equal(host(wgts), ow, "wgts"); assert_close(host(outs), oo, "outs")
+    ogx = oracle.trilinear_devoxelize_backward(gy, oi, ow, res)
+    assert_close(host(be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), cu(coords), res)), ogx, "grad (coords)", atol_frac=1e-5)
+    assert_close(host(be.pvcnn.trilinear_devoxelize_backward(cu(gy), inds, wgts, res)), ogx, "grad (generic)", atol_frac=1e-5)
+
+
+def test_resolution_64_plane_outside_shared_memory(be, oracle):
+    """BASELINE config 5 resolution r=64: a voxel plane is 1 MB, read through L2 instead of shared memory."""
+    coords, vox, gy, res = cases.devox_case(seed=81, b=1, c=2, n=3000, res=64)
+    outs, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(coords), cu(vox))
+    oo, oi, ow = oracle.trilinear_devoxelize_forward(res, coords, vox)
+    assert_equal(host(inds), oi, "inds"); assert_equal(host(wgts), ow, "wgts"); assert_close(host(outs), oo, "outs")
+    from pcfm.functional import trilinear_devoxelize
+    v = cu(vox).view(1, 2, res, res, res).requires_grad_(True)
+    trilinear_devoxelize(v, cu(coords), res, True).backward(cu(gy))       # r > 37: generic backward entry
+    assert_close(host(v.grad).reshape(1, 2, -1), oracle.trilinear_devoxelize_backward(gy, oi, ow, res), "grad", atol_frac=1e-5)
+    feat, c2, _ = cases.voxel_case(seed=82, b=1, c=2, n=3000, res=64)
+    vc, _ = gpu_voxel_coords(c2, 64)
+    out, ind, cnt = be.pvcnn.avg_voxelize_forward(cu(feat), vc, 64)
+    o_out, o_ind, o_cnt = oracle.avg_voxelize_forward(feat, host(vc), 64)
+    assert_equal(host(ind), o_ind, "ind"); assert_equal(host(cnt), o_cnt, "cnt"); assert_close(host(out), o_out, "out")
+    gx = be.pvcnn.avg_voxelize_backward(cu(rng(83).standard_normal(o_out.shape).astype(np.float32)), ind, cnt)
+    assert gx.shape == (1, 2, 3000)
