@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--ops", default="")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: r x N x C sweep (B=2)")
     args = ap.parse_args()
     only = set(args.only.split(",")) if args.only else None
     ref = None
@@ -46,10 +47,12 @@ def main():
     g = torch.Generator(device=dev).manual_seed(0)
     B, N = 8, 20000
     rows = []
-    for name, c, r in [("s1", 128, 32), ("s2", 256, 16), ("s3", 256, 8), ("c1", 64, 32)]:
+    shapes = [("s1", 128, 32, B, N), ("s2", 256, 16, B, N), ("s3", 256, 8, B, N), ("c1", 64, 32, 2, 2048)]
+    if args.sweep:
+        shapes = [(f"c5_r{r}_n{n}_c{c}", c, r, 2, n) for r in (16, 32, 64) for n in (10000, 20000, 100000) for c in (64, 256)]
+    for name, c, r, b, n in shapes:
         if only and name not in only:
             continue
-        b, n = (2, 2048) if name == "c1" else (B, N)
         feat = torch.randn(b, c, n, device=dev, generator=g)
         if args.kind == "randn":
             coords = torch.randn(b, 3, n, device=dev, generator=g)
@@ -72,7 +75,8 @@ def main():
             "vox_bwd": lambda: P.avg_voxelize_backward(grid, ind, cnt),
             "devox_fwd": lambda: P.trilinear_devoxelize_forward(r, True, nc, grid),
             "devox_fwd_eval": lambda: P.trilinear_devoxelize_forward(r, False, nc, grid),
-            "devox_bwd": lambda: P.trilinear_devoxelize_backward_coords(gy, nc, r),
+            "devox_bwd": (lambda: P.trilinear_devoxelize_backward_coords(gy, nc, r)) if r <= P.MAX_FAST_DEVOX_BWD_R
+            else (lambda: P.trilinear_devoxelize_backward(gy, inds, wgts, r)),
             "devox_bwd_generic": lambda: P.trilinear_devoxelize_backward(gy, inds, wgts, r),
         }
         if args.ops:
@@ -105,6 +109,8 @@ def main():
                 row["ms_reference_cuda"] = round(timeit(rf, iters=3, warm=1), 3)
             rows.append(row)
             print(json.dumps(row), flush=True)
+    if args.sweep:
+        only = {"none"}
     if not only or "chamfer" in only:
         for (b, n, m) in [(32, 2000, 1000), (2, 2048, 2048), (8, 20000, 20000)]:
             a = torch.rand(b, n, 3, device=dev, generator=g); c2 = torch.rand(b, m, 3, device=dev, generator=g)
@@ -126,7 +132,8 @@ def main():
                 row["ms_reference_cuda"] = round(timeit(lambda: E.matchcost_forward(a, c2, E.approxmatch_forward(a, c2)), iters=3, warm=1), 3)
             rows.append(row); print(json.dumps(row), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", f"perf_ops_{args.kind}.json"), "w"), indent=1)
+    tag = "sweep_" + args.kind if args.sweep else args.kind
+    json.dump(rows, open(os.path.join(ROOT, "gpurun_out", f"perf_ops_{tag}.json"), "w"), indent=1)
 
 
 if __name__ == "__main__":
