@@ -506,3 +506,28 @@ def test_resolution_64_plane_outside_shared_memory(be, oracle):
     assert_equal(host(ind), o_ind, "ind"); assert_equal(host(cnt), o_cnt, "cnt"); assert_close(host(out), o_out, "out")
     gx = be.pvcnn.avg_voxelize_backward(cu(rng(83).standard_normal(o_out.shape).astype(np.float32)), ind, cnt)
     assert gx.shape == (1, 2, 3000)
+
+
+def test_cuda_graph_capture_of_a_pvconv_primitive_chain(be):
+    """Every launcher runs on the caller's stream and never synchronises, so a sampler step can be captured into a
+    CUDA graph and replayed (the reference launches 14 of its 20 kernels on the legacy stream and cannot)."""
+    feat, coords, res = cases.voxel_case(seed=91, b=2, c=8, n=3000, res=16)
+    f = cu(feat)
+    vox, nc = gpu_voxel_coords(coords, res)
+    nc = nc.contiguous()
+    eager = be.pvcnn.trilinear_devoxelize_forward(res, False, nc, be.pvcnn.avg_voxelize_forward(f, vox, res)[0])[0]
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        for _ in range(2):   # warm-up on the side stream (one-time cudaFuncSetAttribute calls happen here)
+            be.pvcnn.trilinear_devoxelize_forward(res, False, nc, be.pvcnn.avg_voxelize_forward(f, vox, res)[0])
+    torch.cuda.current_stream().wait_stream(s)
+    with torch.cuda.graph(g):
+        grid = be.pvcnn.avg_voxelize_forward(f, vox, res)[0]
+        out = be.pvcnn.trilinear_devoxelize_forward(res, False, nc, grid)[0]
+    f.mul_(2.0)          # new input values, same buffers
+    g.replay()
+    torch.cuda.synchronize()
+    assert_close(host(out), 2.0 * host(eager), "graph replay on updated inputs", rtol=1e-6, atol_frac=1e-6)
