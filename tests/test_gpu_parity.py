@@ -531,3 +531,64 @@ def test_cuda_graph_capture_of_a_pvconv_primitive_chain(be):
     g.replay()
     torch.cuda.synchronize()
     assert_close(host(out), 2.0 * host(eager), "graph replay on updated inputs", rtol=1e-6, atol_frac=1e-6)
+
+
+# ------------------------------------------------------------------------------------------------ randomized shapes
+def test_random_small_shapes_pvconv_primitives(be, oracle):
+    """40 random (B, C, N, r) combinations, odd sizes included: ragged tails, unaligned rows (no TMA), r not a power
+    of two, fewer points than a warp, more voxels than points and vice versa."""
+    r0 = rng(1001)
+    for it in range(40):
+        b = int(r0.integers(1, 4)); c = int(r0.integers(1, 20)); n = int(r0.integers(1, 700)); res = int(r0.integers(2, 21))
+        feat, coords, _ = cases.voxel_case(seed=2000 + it, b=b, c=c, n=n, res=res, kind="randn" if it % 2 else "clustered")
+        vox, nc = gpu_voxel_coords(coords, res)
+        tag = f"[it={it} b={b} c={c} n={n} r={res}]"
+        out, ind, cnt = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res)
+        o_out, o_ind, o_cnt = oracle.avg_voxelize_forward(feat, host(vox), res)
+        assert_equal(host(ind), o_ind, "ind " + tag); assert_equal(host(cnt), o_cnt, "cnt " + tag)
+        assert_close(host(out), o_out, "vox out " + tag)
+        gy = r0.standard_normal(o_out.shape).astype(np.float32)
+        assert_equal(host(be.pvcnn.avg_voxelize_backward(cu(gy), ind, cnt)), oracle.avg_voxelize_backward(gy, o_ind, o_cnt), "vox grad " + tag)
+        ncf = host(nc).astype(np.float32)
+        outs, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(ncf), out)
+        oo, oi, ow = oracle.trilinear_devoxelize_forward(res, ncf, host(out))
+        assert_equal(host(inds), oi, "inds " + tag); assert_equal(host(wgts), ow, "wgts " + tag)
+        assert_close(host(outs), oo, "devox out " + tag)
+        g2 = r0.standard_normal(oo.shape).astype(np.float32)
+        ogx = oracle.trilinear_devoxelize_backward(g2, oi, ow, res)
+        assert_close(host(be.pvcnn.trilinear_devoxelize_backward_coords(cu(g2), cu(ncf), res)), ogx, "devox grad (coords) " + tag, atol_frac=1e-5)
+        assert_close(host(be.pvcnn.trilinear_devoxelize_backward(cu(g2), inds, wgts, res)), ogx, "devox grad (generic) " + tag, atol_frac=1e-5)
+
+
+def test_random_small_shapes_metrics_and_pointnet_ops(be, oracle):
+    r0 = rng(1002)
+    for it in range(25):
+        b = int(r0.integers(1, 4)); n = int(r0.integers(1, 600)); m = int(r0.integers(1, 600))
+        kind = ["randn", "rand", "lattice"][it % 3]
+        a, c = cases.cloud_pair(seed=3000 + it, b=b, n=n, m=m, kind=kind)
+        tag = f"[it={it} b={b} n={n} m={m} {kind}]"
+        d1, d2, i1, i2 = run_chamfer(be.chamfer, a, c)
+        od1, od2, oi1, oi2 = oracle.chamfer_forward(a, c)
+        assert_equal(host(i1), oi1, "idx1 " + tag); assert_equal(host(i2), oi2, "idx2 " + tag)
+        assert_equal(host(d1), od1, "dist1 " + tag); assert_equal(host(d2), od2, "dist2 " + tag)
+        cd = host(be.chamfer3d_allpairs(cu(a), cu(c)))
+        want = od1.astype(np.float64).mean(1)[:, None] * 0  # filled below
+        for i in range(b):
+            for j in range(b):
+                e1, e2, _, _ = oracle.chamfer_forward(a[i:i + 1], c[j:j + 1])
+                w = e1.astype(np.float64).mean() + e2.astype(np.float64).mean()
+                assert abs(cd[i, j] - w) <= 1e-5 * max(abs(w), 1e-12), ("allpairs " + tag, i, j, cd[i, j], w)
+    for it in range(12):
+        b = int(r0.integers(1, 3)); n = int(r0.integers(3, 500)); m = int(r0.integers(1, min(n, 120) + 1)); c = int(r0.integers(1, 9))
+        pts, feat, cfeat = cases.pointnet_case(seed=4000 + it, b=b, c=c, n=n, m=m, kind="lattice" if it % 2 else "rand")
+        tag = f"[it={it} b={b} c={c} n={n} m={m}]"
+        fidx = be.pvcnn.furthest_point_sampling(cu(pts), m)
+        assert_equal(host(fidx), oracle.furthest_point_sampling(pts, m), "fps " + tag)
+        ctr = be.pvcnn.gather_features_forward(cu(pts), fidx)
+        u = int(r0.integers(1, 20)); rad = float(r0.uniform(0.05, 0.6))
+        bq = be.pvcnn.ball_query(ctr, cu(pts), rad, u)
+        assert_equal(host(bq), oracle.ball_query(host(ctr), pts, rad, u), "ball query " + tag)
+        o3, i3, w3 = be.pvcnn.three_nearest_neighbors_interpolate_forward(cu(pts), ctr, cu(cfeat))
+        oo3, oi3, ow3 = oracle.three_nn_interpolate_forward(pts, host(ctr), cfeat)
+        assert_equal(host(i3), oi3, "3nn idx " + tag); assert_equal(host(w3), ow3, "3nn w " + tag)
+        assert_close(host(o3), oo3, "3nn out " + tag)
