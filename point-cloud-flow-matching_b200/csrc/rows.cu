@@ -130,28 +130,41 @@ __global__ void __launch_bounds__(1024, 1)
   const float* wb = HAS_W ? w + (long long)b * K * J : nullptr;
   float* ob = out + ((long long)b * C + c0) * J;
   const unsigned pmax = (unsigned)(P - 1);
-  for (int j = threadIdx.x; j < J; j += blockDim.x) {
-    unsigned id[K];
-    float wk[K];
+  // U outputs per thread and iteration: all index / weight loads of the U outputs are issued before the first gather
+  constexpr int U = (K == 1) ? 4 : 2;
+  for (int j0 = threadIdx.x; j0 < J; j0 += blockDim.x * U) {
+    unsigned id[U][K];
+    float wk[U][K];
 #pragma unroll
-    for (int k = 0; k < K; ++k) {
-      id[k] = min((unsigned)ib[(long long)k * J + j], pmax);  // memory safety only; valid indices unchanged
-      wk[k] = HAS_W ? wb[(long long)k * J + j] : 1.f;
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * blockDim.x;
+#pragma unroll
+      for (int k = 0; k < K; ++k) {
+        // min(): memory safety only; valid indices are unchanged
+        id[u][k] = (j < J) ? min((unsigned)ib[(long long)k * J + j], pmax) : 0u;
+        wk[u][k] = (HAS_W && j < J) ? wb[(long long)k * J + j] : 1.f;
+      }
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      float f[K];
+    for (int u = 0; u < U; ++u) {
+      const int j = j0 + u * blockDim.x;
+      if (j >= J) break;
 #pragma unroll
-      for (int k = 0; k < K; ++k) f[k] = PLANE_SMEM ? smem[g * P + id[k]] : __ldg(pg + (long long)g * P + id[k]);
-      float acc;
-      if (K == 1) {
-        acc = HAS_W ? __fmul_rn(f[0], wk[0]) : f[0];
-      } else {
-        acc = f[0] * wk[0];
+      for (int g = 0; g < G; ++g) {
+        float f[K];
 #pragma unroll
-        for (int k = 1; k < K; ++k) acc = fmaf(f[k], wk[k], acc);
+        for (int k = 0; k < K; ++k)
+          f[k] = PLANE_SMEM ? smem[g * P + id[u][k]] : __ldg(pg + (long long)g * P + id[u][k]);
+        float acc;
+        if (K == 1) {
+          acc = HAS_W ? __fmul_rn(f[0], wk[u][0]) : f[0];
+        } else {
+          acc = f[0] * wk[u][0];
+#pragma unroll
+          for (int k = 1; k < K; ++k) acc = fmaf(f[k], wk[u][k], acc);
+        }
+        ob[(long long)g * J + j] = acc;
       }
-      ob[(long long)g * J + j] = acc;
     }
   }
 }
