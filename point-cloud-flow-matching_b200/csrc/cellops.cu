@@ -52,10 +52,10 @@ __global__ void __launch_bounds__(1024, 2)
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
   const int* rc = rec + (long long)b * rcap;
-  const int nl = meta[b * kMetaInts + 15];  // mean plans use a single class: [0, lend[7])
+  const int nl = meta[b * kMetaInts + 0];
   for (int ci = threadIdx.x; ci < nl; ci += blockDim.x) {
     const int d = cl[ci];
-    const int n = d >> 24, t = d & 0xffffff;
+    const int n = (int)((unsigned)d >> 24), t = d & 0xffffff;
     if (n == 0) continue;  // alignment hole
     const int s0 = sl[ci] & 0xffffff;
     const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
@@ -74,11 +74,11 @@ __global__ void __launch_bounds__(1024, 2)
     }
     o[t] = acc;
   }
-  const int nh = meta[b * kMetaInts + 24];
+  const int nh = meta[b * kMetaInts + 1];
   const int lane = threadIdx.x & 31;
   for (int h = threadIdx.x >> 5; h < nh; h += blockDim.x >> 5) {
-    const int* hd = heavy + ((long long)b * hcap + h) * 3;
-    const int t = hd[0], s0 = hd[1], n = hd[2];
+    const int4 hd = ((const int4*)heavy)[(long long)b * hcap + h];
+    const int t = hd.x, s0 = hd.y, n = hd.z;
     const float rcp = __frcp_rn((float)n);
     float acc = 0.f;
     for (int i = lane; i < n; i += 32) {
@@ -147,9 +147,7 @@ __global__ void __launch_bounds__(1024, 1)
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
   const float4* rc = rec + (long long)b * rcap;
-  __shared__ int mt[kMetaInts];
-  if (threadIdx.x < kMetaInts) mt[threadIdx.x] = meta[b * kMetaInts + threadIdx.x];
-  __syncthreads();
+  const int l1 = meta[b * kMetaInts + 0], h1 = meta[b * kMetaInts + 1];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   int off[8];
 #pragma unroll
@@ -158,10 +156,9 @@ __global__ void __launch_bounds__(1024, 1)
   // registers, then adds them into the plane.  Neighbouring cells share voxels, so the add is a shared-memory
   // atomicAdd (a CAS loop on sm_100a; collisions need two adjacent cells to finish in the same few cycles).
   {
-    const int l1 = mt[15];
     for (int ci = threadIdx.x; ci < l1; ci += blockDim.x) {
       const int d = cl[ci];
-      const int n = d >> 24;
+      const int n = (int)((unsigned)d >> 24);
       if (n == 0) continue;  // alignment hole
       const int cell = d & 0xffffff;
       const unsigned se = (unsigned)sl[ci];
@@ -207,10 +204,9 @@ __global__ void __launch_bounds__(1024, 1)
   // Heavy cells: one warp per cell; the 8 partial sums are reduced by recursive halving (9 shuffles instead of 40):
   // after the exchange lane l holds the total of corner (l >> 2) & 7.
   {
-    const int h1 = mt[24];
     for (int h = wid; h < h1; h += nw) {
-      const int* hd = heavy + ((long long)b * hcap + h) * 3;
-      const int cell = hd[0], s0 = hd[1], n = hd[2];
+      const int4 hd = ((const int4*)heavy)[(long long)b * hcap + h];
+      const int cell = hd.x, s0 = hd.y, n = hd.z;
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int i = lane; i < n; i += 32) {
         const float4 q0 = rc[s0 + i];
@@ -241,8 +237,7 @@ __global__ void __launch_bounds__(1024, 1)
       a1 += __shfl_xor_sync(0xffffffffu, a1, 1);
       if ((lane & 3) == 0) {
         const int k = lane >> 2;  // bit 4 of the lane -> dx, bit 3 -> dy, bit 2 -> dz
-        const int cx = cell / r2, cy = (cell / r) % r, cz = cell % r;
-        if (cx + (k >> 2) < r && cy + ((k >> 1) & 1) < r && cz + (k & 1) < r) atomicAdd(plane + cell + off[k], a1);
+        if ((hd.w >> k) & 1) atomicAdd(plane + cell + (k >> 2) * r2 + ((k >> 1) & 1) * r + (k & 1), a1);
       }
     }
   }

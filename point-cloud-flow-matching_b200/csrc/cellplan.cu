@@ -3,8 +3,6 @@
 
 namespace pcfm {
 
-constexpr int kEllPad = 8 * 32 * (kLightMax * (kLightMax + 1) / 2) + 1024;  // every (class, count) bin wastes < 1 slice
-
 __device__ __forceinline__ int floor_cell(const float* cb, int i, int n, int r, float* fx, float* fy, float* fz) {
   // identical arithmetic to devox_fwd_kernel (devox.cu): clamp (no-op for contractual inputs), floor, fraction
   const float hi = (float)(r - 1);
@@ -54,28 +52,25 @@ __global__ void __launch_bounds__(256) cp_count_kernel(const int* __restrict__ v
   if (inb) rank[base + i] = myrank;
 }
 
-// counters per batch element: for parity class q (0..7): ctr[q*kCls + c] = #light cells with c points (c in
-// 1..kLightMax), ctr[q*kCls + kLightMax+1] = #heavy cells; ctr[8*kCls] = #points in heavy cells (allocator of their
-// contiguous record ranges)
-constexpr int kCls = kLightMax + 2;            // per-class counter stride: [1..kLightMax] light bins, [kLightMax+1] heavy cells
-constexpr int kCtr = 8 * kCls + 4;             // [8*kCls] = points in heavy cells
-constexpr int kBins = 8 * kLightMax;  // (class, count) bins in processing order: class-major, count descending
+// counters per batch element: ctr[c] = #light cells with c points (c in 1..light_max), ctr[kLightCap+1] = #heavy
+// cells, ctr[kLightCap+2] = #points in heavy cells (allocator of their contiguous record ranges)
+constexpr int kCtr = kLightCap + 4;
+constexpr int kEllPad = 32 * (kLightCap * (kLightCap + 1) / 2) + 1024;  // every count bin wastes < 1 slice
 
-// mode: 0 = no grid structure needed (mean plans), 1 = corner mask only, 2 = corner mask + parity class
-__device__ __forceinline__ int parity_class(int v, int r, int mode, int* mask) {
-  if (mode == 0) { *mask = 0xff; return 0; }
+// which of the 8 corners (dx,dy,dz) of cell v stay inside the grid (trilinear plans; mean plans do not use it)
+__device__ __forceinline__ int corner_mask(int v, int r, bool tri) {
+  if (!tri) return 0xff;
   const int r2 = r * r;
   const int x = v / r2, y = (v / r) % r, z = v % r;
   int m = 0;
 #pragma unroll
-  for (int k = 0; k < 8; ++k)  // corner k = (dx,dy,dz) exists if it stays inside the grid
+  for (int k = 0; k < 8; ++k)
     if (x + (k >> 2) < r && y + ((k >> 1) & 1) < r && z + (k & 1) < r) m |= 1 << k;
-  *mask = m;
-  return mode == 2 ? (((x & 1) << 2) | ((y & 1) << 1) | (z & 1)) : 0;
+  return m;
 }
 
-// one thread per cell: position inside its (class, count) bin (light) or inside its class's heavy list + a record range
-__global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict__ cnt, int t, int r, int parity,
+// one thread per cell: position inside its count bin (light) or inside the heavy list + a record range
+__global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict__ cnt, int t, int lm,
                                                           int* __restrict__ ctr, int* __restrict__ aux,
                                                           int* __restrict__ recbase) {
   const int b = blockIdx.y;
@@ -83,77 +78,66 @@ __global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict_
   if (v >= t) return;
   const int n = cnt[(long long)b * t + v];
   if (n <= 0) return;
-  int mask;
-  const int q = parity_class(v, r, parity, &mask);
-  int* c = ctr + b * kCtr + q * kCls;
-  if (n <= kLightMax) {
+  int* c = ctr + b * kCtr;
+  if (n <= lm) {
     aux[(long long)b * t + v] = atomicAdd(c + n, 1);
   } else {
-    aux[(long long)b * t + v] = atomicAdd(c + kLightMax + 1, 1);
-    recbase[(long long)b * t + v] = atomicAdd(ctr + b * kCtr + 8 * kCls, n);  // stride-1 record range
+    aux[(long long)b * t + v] = atomicAdd(c + kLightCap + 1, 1);
+    recbase[(long long)b * t + v] = atomicAdd(c + kLightCap + 2, n);  // stride-1 record range
   }
 }
 
 // one thread per cell: sorted index of a light cell, its slice and the slice's record base; heavy list entry
-__global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ cnt, int t, int r, int parity,
+__global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ cnt, int t, int r, int tri, int lm,
                                                         const int* __restrict__ ctr, const int* __restrict__ aux,
                                                         int* __restrict__ recbase, int* __restrict__ cells,
                                                         int* __restrict__ slot0, int* __restrict__ meta,
                                                         int* __restrict__ heavy, int lcap, int hcap) {
-  __shared__ int P[kBins + 1];   // sorted index where bin j starts (class starts are multiples of 32)
-  __shared__ int F[kBins + 1];   // first slice that STARTS in bin j
-  __shared__ int Bs[kBins + 1];  // record offset of slice F[j]
-  __shared__ int H[9];           // heavy list offset of class q
+  // bins in processing order: bin j holds the cells with lm - j points (count descending)
+  __shared__ int P[kLightCap + 1];   // sorted index where bin j starts
+  __shared__ int F[kLightCap + 1];   // first slice that STARTS in bin j
+  __shared__ int Bs[kLightCap + 1];  // record offset of slice F[j]
   __shared__ int c[kCtr];
   const int b = blockIdx.y;
-  for (int i = threadIdx.x; i < kCtr; i += blockDim.x) c[i] = ctr[b * kCtr + i];  // coalesced, not 270 serial reads
+  for (int i = threadIdx.x; i < kCtr; i += blockDim.x) c[i] = ctr[b * kCtr + i];
   __syncthreads();
   if (threadIdx.x == 0) {
-    int p = 0, base = 0, h = 0;
-    for (int q = 0; q < 8; ++q) {
-      p = (p + 31) & ~31;  // a slice never mixes parity classes
-      if (blockIdx.x == 0) meta[b * kMetaInts + q] = min(p, lcap);
-      for (int k = kLightMax; k >= 1; --k) {
-        const int j = q * kLightMax + (kLightMax - k);
-        P[j] = p;
-        F[j] = (p + 31) >> 5;
-        Bs[j] = base;
-        p += c[q * kCls + k];
-        const int pn = (k == 1) ? ((p + 31) & ~31) : p;  // where the next bin starts
-        base += 32 * k * (((pn + 31) >> 5) - F[j]);
-      }
-      if (blockIdx.x == 0) meta[b * kMetaInts + 8 + q] = min(p, lcap);
-      H[q] = h;
-      if (blockIdx.x == 0) meta[b * kMetaInts + 16 + q] = min(h, hcap);
-      h += c[q * kCls + kLightMax + 1];
+    int p = 0, base = 0;
+    for (int k = lm; k >= 1; --k) {
+      const int j = lm - k;
+      P[j] = p;
+      F[j] = (p + 31) >> 5;
+      Bs[j] = base;
+      p += c[k];
+      const int pn = (k == 1) ? ((p + 31) & ~31) : p;  // where the next bin starts
+      base += 32 * k * (((pn + 31) >> 5) - F[j]);      // slices that start in bin j are k records wide
     }
-    P[kBins] = (p + 31) & ~31;
-    F[kBins] = P[kBins] >> 5;
-    H[8] = h;
-    if (blockIdx.x == 0) meta[b * kMetaInts + 24] = min(h, hcap);
+    P[lm] = (p + 31) & ~31;
+    F[lm] = P[lm] >> 5;
+    if (blockIdx.x == 0) {
+      meta[b * kMetaInts + 0] = min(P[lm], lcap);
+      meta[b * kMetaInts + 1] = min(c[kLightCap + 1], hcap);
+    }
   }
   __syncthreads();
   const int v = blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= t) return;
   const int n = cnt[(long long)b * t + v];
   if (n <= 0) return;
-  int mask;
-  const int q = parity_class(v, r, parity, &mask);
-  if (n > kLightMax) {
-    const int slot = H[q] + aux[(long long)b * t + v];
-    if (slot < hcap) {
-      int* hd = heavy + ((long long)b * hcap + slot) * 3;
-      hd[0] = v; hd[1] = recbase[(long long)b * t + v]; hd[2] = n;
-    }
+  const int mask = corner_mask(v, r, tri != 0);
+  if (n > lm) {
+    const int slot = aux[(long long)b * t + v];
+    if (slot < hcap)
+      ((int4*)heavy)[(long long)b * hcap + slot] = make_int4(v, recbase[(long long)b * t + v], n, mask);
     return;
   }
-  int j = q * kLightMax + (kLightMax - n);
+  int j = lm - n;
   const int si = P[j] + aux[(long long)b * t + v];
   const int s = si >> 5, lane = si & 31;
-  while (s < F[j]) --j;  // the bin in which slice s starts (same parity class: class starts are slice aligned)
-  const int width = kLightMax - (j % kLightMax);
-  const int s0 = c[8 * kCls] + Bs[j] + 32 * width * (s - F[j]) + lane;  // the ELL area follows the heavy records
-  recbase[(long long)b * t + v] = s0 | (int)0x80000000;            // stride 32
+  while (s < F[j]) --j;  // the bin in which slice s starts
+  const int width = lm - j;
+  const int s0 = c[kLightCap + 2] + Bs[j] + 32 * width * (s - F[j]) + lane;  // the ELL area follows the heavy records
+  recbase[(long long)b * t + v] = s0 | (int)0x80000000;                     // stride 32
   if (si < lcap) {
     cells[(long long)b * lcap + si] = (n << 24) | v;
     slot0[(long long)b * lcap + si] = (mask << 24) | s0;
@@ -196,8 +180,8 @@ __global__ void __launch_bounds__(256) cp_order_kernel(const int* __restrict__ c
                                                        int lcap, int rcap) {
   const int b = blockIdx.y;
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ci >= meta[b * kMetaInts + 15]) return;  // end of the last class
-  const int n = cells[(long long)b * lcap + ci] >> 24;
+  if (ci >= meta[b * kMetaInts + 0]) return;
+  const int n = (int)((unsigned)cells[(long long)b * lcap + ci] >> 24);
   if (n < 2 || n > kSortMax) return;
   const long long s0 = (long long)b * rcap + (slot0[(long long)b * lcap + ci] & 0xffffff);
   if (TRI) {
@@ -229,14 +213,14 @@ __global__ void __launch_bounds__(256) cp_order_kernel(const int* __restrict__ c
   }
 }
 
-static long long lcap_of(long long n, long long t) { return (((n < t ? n : t) + 31) & ~31LL) + 8 * 32; }
+static long long lcap_of(long long n, long long t) { return (((n < t ? n : t) + 31) & ~31LL) + 32; }
 
 size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear) {
   size_t s = 0;
-  const long long lcap = lcap_of(n, t), hcap = n / (kLightMax + 1) + 1, rcap = n + kEllPad;
+  const long long lcap = lcap_of(n, t), hcap = n / (kLightMaxMean + 1) + 1, rcap = n + kEllPad;
   s += align256((size_t)b * lcap * 4) * 2 + align256((size_t)b * kCtr * 4);  // cells (+counters), slot0
   s += align256((size_t)b * kMetaInts * 4);                    // meta
-  s += align256((size_t)b * hcap * 3 * 4);                     // heavy
+  s += align256((size_t)b * hcap * 4 * 4);                     // heavy
   s += align256((size_t)b * rcap * (trilinear ? 16 : 4));      // rec
   s += align256((size_t)b * n * 4);                            // rank
   s += align256((size_t)b * t * 4) * 2;                        // aux, recbase
@@ -245,10 +229,11 @@ size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear)
 }
 
 int cellplan_build(const int* vox_coords, const float* float_coords, int r, int* ind_out, int b, int n, int t,
-                   int* cnt, CellPlan* plan, Workspace* ws, cudaStream_t st, int parity) {
+                   int* cnt, CellPlan* plan, Workspace* ws, cudaStream_t st) {
   const bool tri = float_coords != nullptr;
   plan->lcap = (int)lcap_of(n, t);
-  plan->hcap = n / (kLightMax + 1) + 1;
+  plan->light_max = tri ? kLightMaxTri : kLightMaxMean;
+  plan->hcap = n / (plan->light_max + 1) + 1;
   plan->rcap = n + kEllPad;
   // cells and the counters are zeroed by ONE memset: they are carved from one block
   const size_t zero_ints = (size_t)b * plan->lcap + (size_t)b * kCtr;
@@ -257,7 +242,7 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
   int* ctr = zero_block ? zero_block + (size_t)b * plan->lcap : nullptr;
   plan->slot0 = ws->take<int>((size_t)b * plan->lcap);
   plan->meta = ws->take<int>((size_t)b * kMetaInts);
-  plan->heavy = ws->take<int>((size_t)b * plan->hcap * 3);
+  plan->heavy = (int*)ws->take<int4>((size_t)b * plan->hcap);
   plan->rec = tri ? (void*)ws->take<float4>((size_t)b * plan->rcap) : (void*)ws->take<int>((size_t)b * plan->rcap);
   int* rank = ws->take<int>((size_t)b * n);
   int* aux = ws->take<int>((size_t)b * t);
@@ -272,31 +257,25 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
     else cp_count_kernel<false><<<gp, 256, 0, st>>>(vox_coords, nullptr, r, ind_out, n, t, cnt, rank);
     PCFM_LAUNCHED();
   }
-  const int mode = tri ? (parity ? 2 : 1) : 0;
-  cp_classify_kernel<<<gt, 256, 0, st>>>(cnt, t, r, mode, ctr, aux, recbase);
+  cp_classify_kernel<<<gt, 256, 0, st>>>(cnt, t, plan->light_max, ctr, aux, recbase);
   PCFM_LAUNCHED();
-  cp_layout_kernel<<<gt, 256, 0, st>>>(cnt, t, r, mode, ctr, aux, recbase, plan->cells, plan->slot0, plan->meta,
+  cp_layout_kernel<<<gt, 256, 0, st>>>(cnt, t, r, tri ? 1 : 0, plan->light_max, ctr, aux, recbase, plan->cells, plan->slot0, plan->meta,
                                        plan->heavy, plan->lcap, plan->hcap);
   PCFM_LAUNCHED();
   if (n > 0) {
-    dim3 gl(cdiv(plan->lcap, 256), b);
     if (tri) {
+      // no ordering pass for trilinear plans: their consumer adds cell sums with shared-memory atomics, whose order
+      // is not fixed anyway
       cp_fill_kernel<true><<<gp, 256, 0, st>>>(nullptr, float_coords, r, n, t, rank, recbase, plan->rec, plan->rcap);
       PCFM_LAUNCHED();
-      // no ordering pass for trilinear plans: their consumer adds cell sums with shared-memory atomics, whose order
-      // is not fixed anyway (the pass costs ~15 us per call; parity != 0 re-enables it for an ordered consumer)
-      if (parity)
-        cp_order_kernel<true><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->meta, plan->rec, plan->lcap,
-                                                  plan->rcap);
-      else
-        --g_launches;
     } else {
+      dim3 gl(cdiv(plan->lcap, 256), b);
       cp_fill_kernel<false><<<gp, 256, 0, st>>>(ind_out, nullptr, r, n, t, rank, recbase, plan->rec, plan->rcap);
       PCFM_LAUNCHED();
       cp_order_kernel<false><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->meta, plan->rec, plan->lcap,
                                                  plan->rcap);
+      PCFM_LAUNCHED();
     }
-    PCFM_LAUNCHED();
   }
   return 0;
 }

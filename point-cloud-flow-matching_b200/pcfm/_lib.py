@@ -3,7 +3,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libpcfm_b200.so")
+# PCFM_B200_LIB: developer override used for A/B builds of the same library (tests/perf_ops.py)
+LIB_PATH = os.environ.get("PCFM_B200_LIB") or os.path.join(os.path.dirname(_HERE), "lib", "libpcfm_b200.so")
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
