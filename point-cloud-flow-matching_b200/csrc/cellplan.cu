@@ -1,5 +1,10 @@
-// cellplan.cu — builds the sliced-ELL cell plan (count -> classify -> layout -> fill -> order).
+// cellplan.cu — builds the sliced-ELL cell plan: count -> classify -> layout -> fill -> order, as one fused kernel
+// (one thread-block cluster per cloud, per-cell table in distributed shared memory) or, for very big grids /
+// clouds, as separate kernels.
 #include "cellplan.cuh"
+
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
 
 namespace pcfm {
 
@@ -172,46 +177,231 @@ __global__ void __launch_bounds__(256) cp_fill_kernel(const int* __restrict__ ke
   }
 }
 
-// one thread per light cell: ascending point order inside the cell (deterministic, and the order the oracle uses)
-template <bool TRI>
+// ascending point order inside one light cell of a mean plan (deterministic, and the order the oracle uses)
+__device__ __forceinline__ void order_cell(int* __restrict__ rr, long long s0, int n) {
+  int loc[kSortMax];
+#pragma unroll
+  for (int a = 0; a < kSortMax; ++a)
+    if (a < n) loc[a] = rr[s0 + 32 * a];
+  for (int a = 1; a < n; ++a) {
+    const int x = loc[a];
+    int j = a - 1;
+    while (j >= 0 && loc[j] > x) { loc[j + 1] = loc[j]; --j; }
+    loc[j + 1] = x;
+  }
+  for (int a = 0; a < n; ++a) rr[s0 + 32 * a] = loc[a];
+}
+
+// one thread per light cell (mean plans)
 __global__ void __launch_bounds__(256) cp_order_kernel(const int* __restrict__ cells,
                                                        const int* __restrict__ slot0,
-                                                       const int* __restrict__ meta, void* __restrict__ rec,
-                                                       int lcap, int rcap) {
+                                                       const int* __restrict__ meta, int* __restrict__ rec, int lcap,
+                                                       int rcap) {
   const int b = blockIdx.y;
   const int ci = blockIdx.x * blockDim.x + threadIdx.x;
   if (ci >= meta[b * kMetaInts + 0]) return;
   const int n = (int)((unsigned)cells[(long long)b * lcap + ci] >> 24);
   if (n < 2 || n > kSortMax) return;
-  const long long s0 = (long long)b * rcap + (slot0[(long long)b * lcap + ci] & 0xffffff);
-  if (TRI) {
-    float4* rr = (float4*)rec;
-    float4 loc[kSortMax];
+  order_cell(rec, (long long)b * rcap + (slot0[(long long)b * lcap + ci] & 0xffffff), n);
+}
+
+// -------------------------------------------------------------------------------------------------
+// Fused build: ONE kernel, one thread-block CLUSTER of kCl CTAs per cloud.  The per-cell table (point counts, later
+// record bases) lives in distributed shared memory: cell v belongs to CTA (v >> 5) % kCl, so the hot cells of a
+// centred cloud are spread over all CTAs; counting is a DSMEM atomicAdd, the phases are separated by cluster
+// barriers instead of kernel boundaries.  Replaces 2 memsets + 4-5 dependent tiny launches (~35 us).
+// (A single CTA per cloud was measured slower than the separate kernels: one SM's load bandwidth is not enough.)
+// -------------------------------------------------------------------------------------------------
+constexpr int kCl = 8;              // CTAs per cluster (portable maximum)
+constexpr int kPlanThreads = 1024;
+constexpr int kPlanUnroll = 4;
+constexpr int kNB = kLightCap + 4;  // [1..lm] cells with that many points, [kLightCap+1] heavy cells, [kLightCap+2] their points
+constexpr int kH = kLightCap + 1, kHP = kLightCap + 2;
+
+#ifndef PCFM_PLAN_AGG
+#define PCFM_PLAN_AGG 1
+#endif
+
+__device__ __forceinline__ int cell_owner(int v) { return (v >> 5) % kCl; }
+__device__ __forceinline__ int cell_local(int v) { return (((v >> 5) / kCl) << 5) | (v & 31); }
+
+template <bool TRI>
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
+    cp_cluster_kernel(const int* __restrict__ vox_coords, const float* __restrict__ fcoords, int r,
+                      int* __restrict__ ind_out, int n, int t, int tq, int lm, int* __restrict__ cnt_out,
+                      int* __restrict__ rank, int* __restrict__ cells, int* __restrict__ slot0,
+                      int* __restrict__ meta, int* __restrict__ heavy, void* __restrict__ rec, int lcap, int hcap,
+                      int rcap) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ int tab[];  // [tq] this CTA's share of the per-cell table
+  __shared__ int bin[kNB];      // this CTA's histogram of cell sizes (read by the other CTAs in phase 3)
+  __shared__ int pos[kNB];      // running positions inside this CTA's part of every bin
+  __shared__ int off[kNB];      // where this CTA's part of every bin starts (sum over lower-ranked CTAs)
+  __shared__ int tot[kNB];      // cluster-wide histogram
+  __shared__ int P[kLightCap + 1], F[kLightCap + 1], Bs[kLightCap + 1];
+  __shared__ int p_end;
+  const int q = (int)cluster.block_rank(), b = blockIdx.x / kCl;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const long long base = (long long)b * n;
+  const float* fb = TRI ? fcoords + base * 3 : nullptr;
+  const int* vb = TRI ? nullptr : vox_coords + base * 3;
+  const int r2 = r * r;
+  const int chunk = (n + kCl - 1) / kCl;
+  const int i_lo = min(n, q * chunk), i_hi = min(n, i_lo + chunk);  // this CTA's points
+  for (int i = tid; i < tq; i += nt) tab[i] = 0;
+  if (tid < kNB) { bin[tid] = 0; pos[tid] = 0; }
+  cluster.sync();
+  // ---- 1. count: cell key of every point, its rank inside the cell ----
+  for (int i0 = i_lo; i0 < i_hi; i0 += nt * kPlanUnroll) {
+    int key[kPlanUnroll];
 #pragma unroll
-    for (int a = 0; a < kSortMax; ++a)
-      if (a < n) loc[a] = rr[s0 + 32 * a];
-    for (int a = 1; a < n; ++a) {
-      const float4 x = loc[a];
-      int j = a - 1;
-      while (j >= 0 && __float_as_int(loc[j].x) > __float_as_int(x.x)) { loc[j + 1] = loc[j]; --j; }
-      loc[j + 1] = x;
+    for (int u = 0; u < kPlanUnroll; ++u) {
+      const int i = i0 + u * nt + tid;
+      key[u] = -1;
+      if (i < i_hi) {
+        if (TRI) {
+          float fx, fy, fz;
+          key[u] = floor_cell(fb, i, n, r, &fx, &fy, &fz);
+        } else {
+          key[u] = vb[i] * r2 + vb[(long long)i + n] * r + vb[(long long)i + 2LL * n];  // vox.cu:31
+        }
+      }
     }
-    for (int a = 0; a < n; ++a) rr[s0 + 32 * a] = loc[a];
-  } else {
-    int* rr = (int*)rec;
-    int loc[kSortMax];
 #pragma unroll
-    for (int a = 0; a < kSortMax; ++a)
-      if (a < n) loc[a] = rr[s0 + 32 * a];
-    for (int a = 1; a < n; ++a) {
-      const int x = loc[a];
-      int j = a - 1;
-      while (j >= 0 && loc[j] > x) { loc[j + 1] = loc[j]; --j; }
-      loc[j + 1] = x;
+    for (int u = 0; u < kPlanUnroll; ++u) {
+      const int i = i0 + u * nt + tid;
+      const bool valid = i < i_hi && key[u] >= 0 && key[u] < t;
+      int rk = -1;
+#if PCFM_PLAN_AGG
+      // lanes of a warp that hit the same cell share one DSMEM atomic (dense clouds: most of a warp at r = 8)
+      const unsigned act = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        const unsigned peers = __match_any_sync(act, key[u]);
+        const int leader = __ffs(peers) - 1, lane = tid & 31;
+        int old = 0;
+        if (lane == leader)
+          old = atomicAdd(cluster.map_shared_rank(tab, cell_owner(key[u])) + cell_local(key[u]), __popc(peers));
+        rk = __shfl_sync(peers, old, leader) + __popc(peers & ((1u << lane) - 1u));
+      }
+#else
+      if (valid) rk = atomicAdd(cluster.map_shared_rank(tab, cell_owner(key[u])) + cell_local(key[u]), 1);
+#endif
+      if (i < i_hi) {
+        rank[base + i] = rk;
+        if (!TRI) ind_out[base + i] = key[u];
+      }
     }
-    for (int a = 0; a < n; ++a) rr[s0 + 32 * a] = loc[a];
+  }
+  cluster.sync();
+  // ---- 2. histogram of the sizes of this CTA's cells (+ the per-cell counts, an output of avg_voxelize) ----
+  for (int l = tid; l < tq; l += nt) {
+    const int v = (((l >> 5) * kCl + q) << 5) | (l & 31);
+    if (v >= t) continue;
+    const int c = tab[l];
+    if (cnt_out) cnt_out[(long long)b * t + v] = c;
+    if (c > 0) atomicAdd(bin + (c <= lm ? c : kH), 1);
+    if (c > lm) atomicAdd(bin + kHP, c);
+  }
+  cluster.sync();
+  // ---- 3. cluster-wide bins, where this CTA's part of each bin starts, where every bin starts ----
+  if (tid < kNB) {
+    int sum = 0, mine = 0;
+#pragma unroll
+    for (int k = 0; k < kCl; ++k) {
+      const int x = cluster.map_shared_rank(bin, k)[tid];
+      if (k == q) mine = sum;
+      sum += x;
+    }
+    tot[tid] = sum;
+    off[tid] = mine;
+  }
+  __syncthreads();
+  if (tid == 0) {  // bins in processing order: bin j holds the cells with lm - j points
+    int p = 0, rb = 0;
+    for (int k = lm; k >= 1; --k) {
+      const int j = lm - k;
+      P[j] = p;
+      F[j] = (p + 31) >> 5;
+      Bs[j] = rb;
+      p += tot[k];
+      const int pn = (k == 1) ? ((p + 31) & ~31) : p;
+      rb += 32 * k * (((pn + 31) >> 5) - F[j]);
+    }
+    p_end = p;
+    P[lm] = (p + 31) & ~31;
+    F[lm] = P[lm] >> 5;
+    if (q == 0) {
+      meta[b * kMetaInts + 0] = min(P[lm], lcap);
+      meta[b * kMetaInts + 1] = min(tot[kH], hcap);
+    }
+  }
+  __syncthreads();
+  // ---- 4. place this CTA's cells: light -> (sorted index, slice, record base), heavy -> list entry + records ----
+  const int hpts = tot[kHP];
+  for (int l = tid; l < tq; l += nt) {
+    const int v = (((l >> 5) * kCl + q) << 5) | (l & 31);
+    if (v >= t) continue;
+    const int c = tab[l];
+    if (c > 0 && c <= lm) {
+      int j = lm - c;
+      const int si = P[j] + off[c] + atomicAdd(pos + c, 1);
+      const int sidx = si >> 5;
+      while (sidx < F[j]) --j;  // the bin in which this slice starts
+      const int s0 = hpts + Bs[j] + 32 * (lm - j) * (sidx - F[j]) + (si & 31);  // the ELL area follows the heavy records
+      tab[l] = s0 | (int)0x80000000;
+      if (si < lcap) {
+        cells[(long long)b * lcap + si] = (c << 24) | v;
+        slot0[(long long)b * lcap + si] = (corner_mask(v, r, TRI) << 24) | s0;
+      }
+    } else if (c > lm) {
+      const int slot = off[kH] + atomicAdd(pos + kH, 1);
+      const int rb = off[kHP] + atomicAdd(pos + kHP, c);
+      tab[l] = rb;
+      if (slot < hcap) ((int4*)heavy)[(long long)b * hcap + slot] = make_int4(v, rb, c, corner_mask(v, r, TRI));
+    }
+  }
+  if (q == 0)
+    for (int si = p_end + tid; si < P[lm] && si < lcap; si += nt) cells[(long long)b * lcap + si] = 0;  // holes
+  cluster.sync();
+  // ---- 5. fill the records of this CTA's points ----
+  for (int i0 = i_lo; i0 < i_hi; i0 += nt * kPlanUnroll) {
+    int rk[kPlanUnroll], key[kPlanUnroll];
+    float fx[kPlanUnroll], fy[kPlanUnroll], fz[kPlanUnroll];
+#pragma unroll
+    for (int u = 0; u < kPlanUnroll; ++u) {
+      const int i = i0 + u * nt + tid;
+      rk[u] = -1;
+      if (i < i_hi) {
+        rk[u] = rank[base + i];
+        if (TRI) key[u] = floor_cell(fb, i, n, r, &fx[u], &fy[u], &fz[u]);
+        else key[u] = ind_out[base + i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kPlanUnroll; ++u) {
+      const int i = i0 + u * nt + tid;
+      if (rk[u] < 0) continue;
+      const int rb = cluster.map_shared_rank(tab, cell_owner(key[u]))[cell_local(key[u])];
+      const int slot = (rb & 0x7fffffff) + rk[u] * (rb < 0 ? 32 : 1);
+      if (slot >= rcap) continue;
+      if (TRI) ((float4*)rec)[(long long)b * rcap + slot] = make_float4(__int_as_float(i), fx[u], fy[u], fz[u]);
+      else ((int*)rec)[(long long)b * rcap + slot] = i;
+    }
+  }
+  cluster.sync();  // records complete (global, cluster scope); no CTA leaves while its table may still be read
+  if (!TRI) {
+    // ---- 6. mean plans: ascending point order inside small cells ----
+    const int l1 = min(P[lm], lcap);
+    for (int ci = q * nt + tid; ci < l1; ci += kCl * nt) {
+      const int c = (int)((unsigned)cells[(long long)b * lcap + ci] >> 24);
+      if (c < 2 || c > kSortMax) continue;
+      order_cell((int*)rec, (long long)b * rcap + (slot0[(long long)b * lcap + ci] & 0xffffff), c);
+    }
   }
 }
+
+constexpr size_t kFusedMaxTable = 220 * 1024;  // per CTA; + ~2 KB static shared memory <= 227 KB
+constexpr int kFusedMaxPoints = 1 << 18;       // beyond this 8 CTAs per cloud are slower than the multi-kernel build
 
 static long long lcap_of(long long n, long long t) { return (((n < t ? n : t) + 31) & ~31LL) + 32; }
 
@@ -249,6 +439,28 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
   int* recbase = ws->take<int>((size_t)b * t);
   if (!cnt) cnt = ws->take<int>((size_t)b * t);
   if (!ws->ok()) return PCFM_E_WORKSPACE;
+  const int tq = (cdiv(cdiv(t, 32), kCl)) * 32;  // cells per CTA of the cluster
+  const size_t tab_bytes = (size_t)tq * sizeof(int);
+  if (g_opt_plan == 0 && n > 0 && n <= kFusedMaxPoints && tab_bytes <= kFusedMaxTable) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      PCFM_CUDA(cudaFuncSetAttribute(cp_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kFusedMaxTable));
+      PCFM_CUDA(cudaFuncSetAttribute(cp_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)kFusedMaxTable));
+      attr_set = true;
+    }
+    if (tri)
+      cp_cluster_kernel<true><<<b * kCl, kPlanThreads, tab_bytes, st>>>(
+          nullptr, float_coords, r, nullptr, n, t, tq, plan->light_max, nullptr, rank, plan->cells, plan->slot0,
+          plan->meta, plan->heavy, plan->rec, plan->lcap, plan->hcap, plan->rcap);
+    else
+      cp_cluster_kernel<false><<<b * kCl, kPlanThreads, tab_bytes, st>>>(
+          vox_coords, nullptr, r, ind_out, n, t, tq, plan->light_max, cnt, rank, plan->cells, plan->slot0,
+          plan->meta, plan->heavy, plan->rec, plan->lcap, plan->hcap, plan->rcap);
+    PCFM_LAUNCHED();
+    return 0;
+  }
   PCFM_CUDA(cudaMemsetAsync(cnt, 0, (size_t)b * t * sizeof(int), st));
   PCFM_CUDA(cudaMemsetAsync(zero_block, 0, zero_ints * sizeof(int), st));  // counters; holes in `cells` = empty
   dim3 gp(cdiv(n > 0 ? n : 1, 256), b), gt(cdiv(t, 256), b);
@@ -272,8 +484,8 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
       dim3 gl(cdiv(plan->lcap, 256), b);
       cp_fill_kernel<false><<<gp, 256, 0, st>>>(ind_out, nullptr, r, n, t, rank, recbase, plan->rec, plan->rcap);
       PCFM_LAUNCHED();
-      cp_order_kernel<false><<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->meta, plan->rec, plan->lcap,
-                                                 plan->rcap);
+      cp_order_kernel<<<gl, 256, 0, st>>>(plan->cells, plan->slot0, plan->meta, (int*)plan->rec, plan->lcap,
+                                          plan->rcap);
       PCFM_LAUNCHED();
     }
   }

@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--ops", default="")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--plan", type=int, default=0, help="pcfm_set_option('plan', .): 1 = multi-kernel cell-plan build")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: r x N x C sweep (B=2)")
     args = ap.parse_args()
     only = set(args.only.split(",")) if args.only else None
@@ -44,6 +45,7 @@ def main():
         from oracle import build_ref
         ref = {k: build_ref.load_ref(k) for k in ("pvcnn", "chamfer", "emd")}
     dev = "cuda"
+    _lib.set_option("plan", args.plan)
     g = torch.Generator(device=dev).manual_seed(0)
     B, N = 8, 20000
     rows = []
@@ -70,7 +72,9 @@ def main():
         s = r ** 3
         byt = {"vox_fwd": 4 * b * (c * n + 3 * n + c * s + n + s), "vox_bwd": 4 * b * (c * s + n + s + c * n),
                "devox_fwd": 4 * b * (3 * n + c * s + c * n + 16 * n), "devox_bwd": 4 * b * (c * n + 16 * n + c * s)}
+        feat0 = feat[:, :0].contiguous()
         ops = {
+            "plan_mean": lambda: P.avg_voxelize_forward(feat0, vox, r),     # C == 0: the cell-plan build alone
             "vox_fwd": lambda: P.avg_voxelize_forward(feat, vox, r),
             "vox_bwd": lambda: P.avg_voxelize_backward(grid, ind, cnt),
             "devox_fwd": lambda: P.trilinear_devoxelize_forward(r, True, nc, grid),

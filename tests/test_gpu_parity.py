@@ -118,6 +118,29 @@ def test_avg_voxelize_stage_variants_agree(be):
     assert_close(host(a[0]), host(b[0]), "TMA-bulk vs plain staging (cells of > 16 points: arrival order)")
 
 
+@pytest.mark.parametrize("res,n", [(32, 20000), (16, 5000), (8, 20000), (3, 50)])
+def test_cell_plan_fused_and_multi_kernel_builds_agree(be, res, n):
+    """The cell plan is built by one fused kernel (per-cell table in shared memory) when the grid fits, else by
+    separate kernels; both must give the same voxelize / devoxelize-backward results."""
+    from pcfm import _lib
+    feat, coords, _ = cases.voxel_case(seed=90 + res, b=2, c=6, n=n, res=res)
+    vox, nc = gpu_voxel_coords(coords, res)
+    gy = cu(rng(91).standard_normal((2, 6, n)).astype(np.float32))
+    a = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res)
+    nc = nc.contiguous()
+    ga = be.pvcnn.trilinear_devoxelize_backward_coords(gy, nc, res)
+    _lib.set_option("plan", 1)
+    try:
+        b = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res)
+        gb = be.pvcnn.trilinear_devoxelize_backward_coords(gy, nc, res)
+    finally:
+        _lib.set_option("plan", 0)
+    assert_equal(host(a[1]), host(b[1]), "ind")
+    assert_equal(host(a[2]), host(b[2]), "cnt")
+    assert_close(host(a[0]), host(b[0]), "voxelize out")
+    assert_close(host(ga), host(gb), "devoxelize backward")
+
+
 # ------------------------------------------------------------------------------------------------ devoxelize
 DEVOX_SHAPES = [
     dict(seed=11, b=2, c=64, n=2048, res=32),
