@@ -148,6 +148,8 @@ DEVOX_SHAPES = [
     dict(seed=13, b=2, c=16, n=20000, res=16),
     dict(seed=14, b=2, c=16, n=20000, res=8),
     dict(seed=15, b=1, c=5, n=7, res=2),
+    dict(seed=18, b=2, c=304, n=3001, res=8),     # enough rows for the two-channels-per-CTA backward (unaligned rows)
+    dict(seed=19, b=2, c=300, n=6000, res=16),    # same, 16-byte aligned rows (TMA staging)
 ]
 
 
