@@ -7,6 +7,13 @@
 #include "cellplan.cuh"
 #include "rows.cuh"
 
+#ifndef PCFM_HEAVY_U
+#define PCFM_HEAVY_U 1
+#endif
+#ifndef PCFM_HEAVY_V
+#define PCFM_HEAVY_V 4
+#endif
+
 namespace pcfm {
 
 // -------------------------------------------------------------------------------------------------
@@ -60,16 +67,15 @@ __global__ void __launch_bounds__(1024, 2)
     const int s0 = sl[ci] & 0xffffff;
     const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
     float acc = 0.f;
-    for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread
-      int p[4];
+    for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread, branch-free tail:
+      int p[4];                          // a padded slot re-reads the last record and contributes an exact +0
 #pragma unroll
-      for (int k = 0; k < 4; ++k) p[k] = (i0 + k < n) ? rc[s0 + 32 * (i0 + k)] : -1;
+      for (int k = 0; k < 4; ++k) p[k] = rc[s0 + 32 * min(i0 + k, n - 1)];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        if (p[k] >= 0) {
-          const float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
-          acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
-        }
+        float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
+        f = (i0 + k < n) ? f : 0.f;
+        acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
       }
     }
     o[t] = acc;
@@ -81,10 +87,16 @@ __global__ void __launch_bounds__(1024, 2)
     const int t = hd.x, s0 = hd.y, n = hd.z;
     const float rcp = __frcp_rn((float)n);
     float acc = 0.f;
-    for (int i = lane; i < n; i += 32) {
-      const int p = rc[s0 + i];
-      const float f = ROW_SMEM ? smem[p] : __ldg(row_g + p);
-      acc = __fadd_rn(acc, __fmul_rn(f, rcp));
+    for (int i = lane; i < n; i += 32 * PCFM_HEAVY_U) {  // PCFM_HEAVY_U independent record loads in flight per lane
+      int p[PCFM_HEAVY_U];
+#pragma unroll
+      for (int k = 0; k < PCFM_HEAVY_U; ++k) p[k] = rc[s0 + min(i + 32 * k, n - 1)];
+#pragma unroll
+      for (int k = 0; k < PCFM_HEAVY_U; ++k) {
+        float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
+        f = (i + 32 * k < n) ? f : 0.f;  // a padded slot contributes an exact +0
+        acc = __fadd_rn(acc, __fmul_rn(f, rcp));
+      }
     }
     acc = warp_sum(acc);
     if (lane == 0) o[t] = acc;
@@ -208,11 +220,17 @@ __global__ void __launch_bounds__(1024, 1)
       const int4 hd = ((const int4*)heavy)[(long long)b * hcap + h];
       const int cell = hd.x, s0 = hd.y, n = hd.z;
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      for (int i = lane; i < n; i += 32) {
-        const float4 q0 = rc[s0 + i];
-        const int p0 = __float_as_int(q0.x);
-        const float g0 = ROW_SMEM ? row[p0] : __ldg(row_g + p0);
-        tri_accumulate(q0.y, q0.z, q0.w, g0, s);
+      for (int i = lane; i < n; i += 32 * PCFM_HEAVY_V) {  // PCFM_HEAVY_V independent record loads in flight per lane
+        float4 q[PCFM_HEAVY_V];
+#pragma unroll
+        for (int k = 0; k < PCFM_HEAVY_V; ++k) q[k] = rc[s0 + min(i + 32 * k, n - 1)];
+#pragma unroll
+        for (int k = 0; k < PCFM_HEAVY_V; ++k) {
+          const int pk = __float_as_int(q[k].x);
+          float gk = ROW_SMEM ? row[pk] : __ldg(row_g + pk);
+          gk = (i + 32 * k < n) ? gk : 0.f;  // a padded slot adds exact zeros
+          tri_accumulate(q[k].y, q[k].z, q[k].w, gk, s);
+        }
       }
       float a4[4], a2[2], a1;
       const bool up16 = lane & 16, up8 = lane & 8, up4 = lane & 4;
