@@ -52,6 +52,15 @@ int pcfm_set_option(const char* key, int value);
  *               kernels vox.cu:18-34,48-72,86-110)
  * ---------------------------------------------------------------------------------------------- */
 
+/* Voxelization.forward tail (third_party/pvcnn/modules/voxelization.py:19-24), one fused kernel instead of six
+ * elementwise torch kernels.  centred f32[B,3,N] = coords - mean over N (voxelization.py:18, computed by the
+ * caller so that the reduction order stays the caller's); scale f32[B] = 2*max||centred|| + eps, or NULL for
+ * normalize=False.  Per element, each step rounded to fp32 exactly like the torch ops it replaces:
+ *   normalize:  v = centred / scale + 0.5        else:  v = (centred + 1) * 0.5
+ *   v = clamp(v * r, 0, r-1)  -> norm_coords f32[B,3,N];   vox_coords i32[B,3,N] = rint(v) (half to even). */
+int pcfm_voxel_coords(const float* centred, const float* scale, int b, int n, int r, float* norm_coords,
+                      int* vox_coords, pcfm_stream_t stream);
+
 /* avg_voxelize_forward (vox.cpp:17-43): features f32[B,C,N], coords i32[B,3,N] (already voxel integers in
  * [0,r-1]) -> out f32[B,C,r^3], ind i32[B,N] (= x*r^2+y*r+z), cnt i32[B,r^3].
  * out[b,c,v] = sum over points with ind==v of features*(1/cnt[v]); empty voxels are 0.

@@ -287,3 +287,38 @@ int pcfm_three_nn_interpolate_forward(const float* points, const float* centers,
 }
 
 }  // extern "C"
+
+// -------------------------------------------------------------------------------------------------
+// Voxelization.forward tail (voxelization.py:19-24): scale, shift, clamp, round — one pass, two outputs
+// -------------------------------------------------------------------------------------------------
+namespace pcfm {
+__global__ void __launch_bounds__(256) voxel_coords_kernel(const float* __restrict__ centred,
+                                                           const float* __restrict__ scale, long long per_batch,
+                                                           float rf, float hi, float* __restrict__ nc,
+                                                           int* __restrict__ vox) {
+  const int b = blockIdx.y;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= per_batch) return;
+  const long long j = (long long)b * per_batch + i;
+  float v = centred[j];
+  if (scale) v = __fadd_rn(__fdiv_rn(v, scale[b]), 0.5f);  // torch: x / tensor is a true division
+  else v = __fmul_rn(__fadd_rn(v, 1.0f), 0.5f);            // (x + 1) / 2.0
+  v = __fmul_rn(v, rf);
+  v = v < 0.f ? 0.f : (v > hi ? hi : v);                   // torch.clamp: NaN stays NaN
+  nc[j] = v;
+  vox[j] = __float2int_rn(v);                              // torch.round = half to even, then .to(int32)
+}
+}  // namespace pcfm
+
+extern "C" int pcfm_voxel_coords(const float* centred, const float* scale, int b, int n, int r, float* norm_coords,
+                                 int* vox_coords, pcfm_stream_t stream) {
+  if (b < 0 || n < 0 || r <= 0) return PCFM_E_BADARG;
+  if (b == 0 || n == 0) return 0;
+  if (!centred || !norm_coords || !vox_coords) return PCFM_E_BADARG;
+  const long long per_batch = 3LL * n;
+  dim3 grid(pcfm::cdiv(per_batch, 256), b);
+  pcfm::voxel_coords_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(centred, scale, per_batch, (float)r,
+                                                                    (float)(r - 1), norm_coords, vox_coords);
+  PCFM_LAUNCHED();
+  return 0;
+}

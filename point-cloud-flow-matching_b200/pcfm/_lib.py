@@ -41,6 +41,7 @@ SIGNATURES = {
     "pcfm_gather_features_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "pcfm_gather_features_backward_workspace": (_sz, [_i, _i, _i, _i]),
     "pcfm_gather_features_backward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_voxel_coords": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "pcfm_furthest_point_sampling_workspace": (_sz, [_i, _i, _i]),
     "pcfm_furthest_point_sampling": (_i, [_p, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_three_nn_interpolate_forward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p]),

@@ -76,6 +76,25 @@ class _PvcnnBackend:
         return [out, ind, cnt]
 
     @staticmethod
+    def voxel_coords(centred, scale, resolution):
+        """Fused tail of Voxelization.forward (modules/voxelization.py:19-24): centred f32[B,3,N] (coords minus their
+        mean), scale f32[B] or None -> (norm_coords f32[B,3,N] in [0,r-1], vox_coords i32[B,3,N])."""
+        _chk(centred, "centred", "f")
+        b, three, n = centred.shape
+        if three != 3:
+            raise RuntimeError("centred must be [B,3,N]")
+        if scale is not None:
+            _chk(scale, "scale", "f")
+            if scale.numel() != b:
+                raise RuntimeError("scale must have B elements")
+        nc = torch.empty_like(centred)
+        vox = torch.empty(centred.shape, dtype=torch.int32, device=centred.device)
+        with torch.cuda.device(centred.device):
+            check(lib.pcfm_voxel_coords(_ptr(centred), _ptr(scale) if scale is not None else None, b, n,
+                                        int(resolution), _ptr(nc), _ptr(vox), _stream(centred)), "voxel_coords")
+        return nc, vox
+
+    @staticmethod
     def avg_voxelize_backward(grad_y, indices, cnt):
         _chk(grad_y, "grad_y", "f")
         _chk(indices, "indices", "i")

@@ -13,7 +13,7 @@ from torch.autograd import Function
 from .backend import pvcnn as _backend
 
 __all__ = ["avg_voxelize", "trilinear_devoxelize", "ball_query", "grouping", "gather", "furthest_point_sample",
-           "logits_mask", "nearest_neighbor_interpolate", "kl_loss", "huber_loss"]
+           "logits_mask", "nearest_neighbor_interpolate", "kl_loss", "huber_loss", "voxel_coords"]
 
 
 class AvgVoxelization(Function):
@@ -117,6 +117,13 @@ trilinear_devoxelize = TrilinearDevoxelization.apply
 grouping = Grouping.apply
 gather = Gather.apply
 nearest_neighbor_interpolate = NeighborInterpolation.apply
+
+
+def voxel_coords(centred, scale, resolution):
+    """Fused elementwise tail of Voxelization.forward (modules/voxelization.py:19-24): centred f32[B,3,N], scale
+    f32[B] or None -> (norm_coords f32[B,3,N], vox_coords i32[B,3,N]).  No gradient (the reference detaches coords)."""
+    with torch.no_grad():
+        return _backend.voxel_coords(centred.contiguous(), None if scale is None else scale.contiguous(), resolution)
 
 
 def ball_query(centers_coords, points_coords, radius, num_neighbors):

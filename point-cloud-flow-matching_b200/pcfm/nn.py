@@ -2,6 +2,9 @@
 (state_dicts of the reference load unchanged): third_party/pvcnn/modules/{voxelization,pvconv,shared_mlp,se,
 ball_query,pointnet,loss}.py.  Dense layers (Conv3d / Conv1d / BatchNorm / Linear) stay cuDNN / cuBLAS calls.
 """
+import threading
+import weakref
+
 import torch
 import torch.nn as nn
 
@@ -11,12 +14,39 @@ __all__ = ["Voxelization", "PVConv", "SharedMLP", "SE3d", "BallQuery", "PointNet
            "PointNetFPModule", "KLLoss"]
 
 
+class _VoxelCoordCache(threading.local):
+    """Per-thread memo of the coordinate work of Voxelization.forward for the LAST coords tensor seen.
+
+    The PVConv layers of one backbone pass the same `coords` tensor object through (pvconv.py:39 returns it
+    unchanged), so every layer after the first repeats identical reductions and elementwise kernels.  An entry is
+    valid only while it is the same tensor object with the same autograd version counter (any in-place write
+    bumps it); the tensor is held by weak reference.  Level 1: centred coords and max norm (shared by all
+    resolutions); level 2: (norm_coords, vox_coords) per (resolution, normalize, eps).
+    """
+
+    def __init__(self):
+        self.ref, self.version, self.centred, self.maxnorm, self.by_cfg = None, -1, None, None, {}
+
+    def entry(self, coords):
+        if self.ref is None or self.ref() is not coords or coords._version != self.version:
+            self.ref, self.version = weakref.ref(coords), coords._version
+            self.centred, self.maxnorm, self.by_cfg = None, None, {}
+        return self
+
+
+_coord_cache = _VoxelCoordCache()
+
+
 class Voxelization(nn.Module):
     """(features[B,C,N], coords[B,3,N]) -> (voxels[B,C,R,R,R], float voxel coords[B,3,N] in [0,R-1]).
 
-    The normalisation stays in torch ops in the reference's order (modules/voxelization.py:16-25): the voxel
-    index is round_half_even() of this result, so a differently ordered reduction could flip indices.
+    modules/voxelization.py:16-25.  The two reductions (mean over N, max norm) stay torch ops in the reference's
+    order — the voxel index is round_half_even() of the result, so a differently ordered reduction could flip
+    indices; the six elementwise ops after them are one kernel (pcfm_voxel_coords, bit-identical to the torch
+    ops).  `Voxelization.cache = False` disables the per-coords memo (see _VoxelCoordCache).
     """
+
+    cache = True
 
     def __init__(self, resolution, normalize=True, eps=0):
         super().__init__()
@@ -24,16 +54,31 @@ class Voxelization(nn.Module):
         self.normalize = normalize
         self.eps = eps
 
-    def forward(self, features, coords):
-        c = coords.detach()
-        nc = c - c.mean(2, keepdim=True)
+    def _coords(self, coords):
+        e = _coord_cache.entry(coords) if Voxelization.cache else _VoxelCoordCache()
+        key = (self.r, bool(self.normalize), float(self.eps))
+        hit = e.by_cfg.get(key)
+        if hit is not None:
+            return hit
+        if e.centred is None:
+            c = coords.detach()
+            e.centred = (c - c.mean(2, keepdim=True)).contiguous()
+        scale = None
         if self.normalize:
-            scale = nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + self.eps
-            nc = nc / scale + 0.5
-        else:
-            nc = (nc + 1) / 2.0
-        nc = torch.clamp(nc * self.r, 0, self.r - 1)
-        vox = torch.round(nc).to(torch.int32)
+            if e.maxnorm is None:
+                e.maxnorm = e.centred.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values
+            scale = (e.maxnorm * 2.0 + self.eps).reshape(-1)
+        if e.centred.is_cuda and e.centred.dtype == torch.float32:
+            nc, vox = F.voxel_coords(e.centred, scale, self.r)
+        else:  # other dtypes: the reference's op sequence (the CUDA kernels themselves are fp32-only)
+            nc = e.centred / scale.view(-1, 1, 1) + 0.5 if self.normalize else (e.centred + 1) / 2.0
+            nc = torch.clamp(nc * self.r, 0, self.r - 1)
+            vox = torch.round(nc).to(torch.int32)
+        e.by_cfg[key] = (nc, vox)
+        return nc, vox
+
+    def forward(self, features, coords):
+        nc, vox = self._coords(coords)
         return F.avg_voxelize(features, vox, self.r), nc
 
     def extra_repr(self):

@@ -456,6 +456,66 @@ def test_pvconv_module_forward_backward_and_eval_contract(be, oracle):
         out2.sum().backward()
 
 
+def _torch_voxel_coords(c, r, normalize, eps):
+    """modules/voxelization.py:17-24 as the reference runs it (torch ops on the GPU)."""
+    nc = c - c.mean(2, keepdim=True)
+    if normalize:
+        nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + eps) + 0.5
+    else:
+        nc = (nc + 1) / 2.0
+    nc = torch.clamp(nc * r, 0, r - 1)
+    return nc, torch.round(nc).to(torch.int32)
+
+
+@pytest.mark.parametrize("r,normalize,eps", [(32, True, 0), (16, True, 1e-6), (8, False, 0), (7, True, 0)])
+def test_voxelization_coords_kernel_is_bit_identical_to_the_torch_ops(be, r, normalize, eps):
+    from pcfm.nn import Voxelization
+    g = torch.Generator(device="cuda").manual_seed(70 + r)
+    c = torch.randn(3, 3, 20001, device="cuda", generator=g) * (0.3 if not normalize else 1.0)
+    # adversarial: coordinates that land exactly on .5 voxel boundaries and on the clamp limits
+    c[0, :, :64] = 0.0
+    c[1, 0, :200] = torch.linspace(-3, 3, 200, device="cuda")
+    t_nc, t_vox = _torch_voxel_coords(c, r, normalize, eps)
+    _, nc = Voxelization(r, normalize, eps)(torch.zeros(3, 1, 20001, device="cuda"), c)
+    assert torch.equal(nc, t_nc), "norm_coords differ from the torch op sequence"
+    centred = (c - c.mean(2, keepdim=True)).contiguous()
+    scale = (centred.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + eps).reshape(-1) if normalize else None
+    k_nc, k_vox = be.pvcnn.voxel_coords(centred, scale, r)
+    assert torch.equal(k_nc, t_nc) and torch.equal(k_vox, t_vox)
+    # half-integers round to even, like torch.round
+    half = torch.tensor([[[0.5, 1.5, 2.5, 3.5, -0.5, 6.49999, 6.5, 1e9]] * 3], device="cuda")
+    k_nc, k_vox = be.pvcnn.voxel_coords((half / r - 0.5).contiguous(), torch.ones(1, device="cuda"), r)
+    e_nc = torch.clamp(((half / r - 0.5) / 1.0 + 0.5) * r, 0, r - 1)
+    assert torch.equal(k_nc, e_nc) and torch.equal(k_vox, torch.round(e_nc).to(torch.int32))
+
+
+def test_voxelization_coordinate_memo(be):
+    """Layers that receive the SAME coords tensor reuse its voxel coordinates; an in-place write invalidates them."""
+    from pcfm import _lib
+    from pcfm.nn import Voxelization
+    c = torch.randn(2, 3, 4000, device="cuda")
+    f = torch.randn(2, 4, 4000, device="cuda")
+    v16, v16b, v8 = Voxelization(16, True, 1e-6), Voxelization(16, True, 1e-6), Voxelization(8, True, 1e-6)
+    _, nc_a = v16(f, c)
+    n0 = _lib.launch_count()
+    _, nc_b = v16b(f, c)                    # other instance, same configuration: memo hit
+    assert nc_b is nc_a and _lib.launch_count() - n0 == 2      # cell plan + voxelize kernel only
+    _, nc_8 = v8(f, c)                      # other resolution: shares the centred coords / max norm
+    assert torch.equal(nc_8, _torch_voxel_coords(c, 8, True, 1e-6)[0])
+    c.mul_(0.5)                             # in-place write bumps the version counter
+    _, nc_c = v16(f, c)
+    assert nc_c is not nc_a and torch.equal(nc_c, _torch_voxel_coords(c, 16, True, 1e-6)[0])
+    _, nc_d = v16(f, c.clone())             # a different tensor object never hits
+    assert nc_d is not nc_c and torch.equal(nc_d, nc_c)
+    Voxelization.cache = False
+    try:
+        _, nc_e = v16(f, c)
+        _, nc_f = v16(f, c)
+        assert nc_e is not nc_f and torch.equal(nc_e, nc_f)
+    finally:
+        Voxelization.cache = True
+
+
 def test_inputs_are_not_mutated_and_streams_are_respected(be):
     feat, coords, res = cases.voxel_case(seed=61, b=2, c=8, n=3000, res=16)
     vox, _ = gpu_voxel_coords(coords, res)
