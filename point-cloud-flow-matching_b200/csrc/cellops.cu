@@ -131,6 +131,7 @@ __global__ void __launch_bounds__(1024, 1)
                           int use_tma) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
+  __shared__ int next_item;
   const int r2 = r * r, P = r2 * r;
   float* plane = smem;                 // [P]
   float* row = smem + ((P + 3) & ~3);  // [N] (ROW_SMEM)
@@ -140,6 +141,7 @@ __global__ void __launch_bounds__(1024, 1)
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
+    next_item = 0;
   }
   __syncthreads();
   const bool aligned = ROW_SMEM && use_tma && ((((uintptr_t)row_g) & 15) == 0);
@@ -160,22 +162,31 @@ __global__ void __launch_bounds__(1024, 1)
   const int* sl = slot0 + (long long)b * lcap;
   const float4* rc = rec + (long long)b * rcap;
   const int l1 = meta[b * kMetaInts + 0], h1 = meta[b * kMetaInts + 1];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int lane = threadIdx.x & 31;
   int off[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) off[k] = (k >> 2) * r2 + ((k >> 1) & 1) * r + (k & 1);
-  // Light cells (count-sorted, sliced-ELL): one thread per cell sums the 8 corner contributions of its points in
-  // registers, then adds them into the plane.  Neighbouring cells share voxels, so the add is a shared-memory
-  // atomicAdd (a CAS loop on sm_100a; collisions need two adjacent cells to finish in the same few cycles).
-  {
-    for (int ci = threadIdx.x; ci < l1; ci += blockDim.x) {
+  // Work items, taken from a shared counter by whole warps (dynamic: the static round-robin left most warps waiting
+  // at the final barrier for the one that drew the longest cells — 3.5-5.6 stalled warps per issue slot in ncu):
+  //   [0, nslice)           slices of 32 light cells, longest cells first (count-sorted plan)
+  //   [nslice, nslice + h1) pieces (<= kHeavyChunk records) of heavy cells
+  const int nslice = l1 >> 5, nitem = nslice + h1;
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&next_item, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitem) break;
+    if (item < nslice) {
+      // Light cells (sliced-ELL): one thread per cell sums the 8 corner contributions of its points in registers,
+      // then adds them into the plane.  Neighbouring cells share voxels, so the add is a shared-memory atomicAdd
+      // (a CAS loop on sm_100a; collisions need two adjacent cells to finish in the same few cycles).
+      const int ci = (item << 5) | lane;
       const int d = cl[ci];
-      const int n = (int)((unsigned)d >> 24);
-      if (n == 0) continue;  // alignment hole
+      const int n = (int)((unsigned)d >> 24);  // 0 = alignment hole
       const int cell = d & 0xffffff;
       const unsigned se = (unsigned)sl[ci];
       const int s0 = se & 0xffffff;
-      const unsigned mask = se >> 24;
+      const unsigned mask = n ? se >> 24 : 0u;
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       // records are walked 4 / 2 / 1 at a time: independent loads in flight, no padded work (slices are count-sorted,
       // so the lanes of a warp take the same path except at slice boundaries)
@@ -211,13 +222,10 @@ __global__ void __launch_bounds__(1024, 1)
 #pragma unroll
       for (int k = 0; k < 8; ++k)
         if ((mask >> k) & 1u) atomicAdd(plane + cell + off[k], s[k]);
-    }
-  }
-  // Heavy cells: one warp per cell; the 8 partial sums are reduced by recursive halving (9 shuffles instead of 40):
-  // after the exchange lane l holds the total of corner (l >> 2) & 7.
-  {
-    for (int h = wid; h < h1; h += nw) {
-      const int4 hd = ((const int4*)heavy)[(long long)b * hcap + h];
+    } else {
+      // Heavy cell piece: the whole warp; the 8 partial sums are reduced by recursive halving (9 shuffles instead
+      // of 40): after the exchange lane l holds the total of corner (l >> 2) & 7.
+      const int4 hd = ((const int4*)heavy)[(long long)b * hcap + (item - nslice)];
       const int cell = hd.x, s0 = hd.y, n = hd.z;
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int i = lane; i < n; i += 32 * PCFM_HEAVY_V) {  // PCFM_HEAVY_V independent record loads in flight per lane

@@ -75,7 +75,7 @@ __device__ __forceinline__ int corner_mask(int v, int r, bool tri) {
 }
 
 // one thread per cell: position inside its count bin (light) or inside the heavy list + a record range
-__global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict__ cnt, int t, int lm,
+__global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict__ cnt, int t, int lm, int chunk,
                                                           int* __restrict__ ctr, int* __restrict__ aux,
                                                           int* __restrict__ recbase) {
   const int b = blockIdx.y;
@@ -87,13 +87,14 @@ __global__ void __launch_bounds__(256) cp_classify_kernel(const int* __restrict_
   if (n <= lm) {
     aux[(long long)b * t + v] = atomicAdd(c + n, 1);
   } else {
-    aux[(long long)b * t + v] = atomicAdd(c + kLightCap + 1, 1);
-    recbase[(long long)b * t + v] = atomicAdd(c + kLightCap + 2, n);  // stride-1 record range
+    aux[(long long)b * t + v] = atomicAdd(c + kLightCap + 1, ((n - 1) / chunk + 1));  // heavy list entries
+    recbase[(long long)b * t + v] = atomicAdd(c + kLightCap + 2, n);                    // stride-1 record range
   }
 }
 
 // one thread per cell: sorted index of a light cell, its slice and the slice's record base; heavy list entry
 __global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ cnt, int t, int r, int tri, int lm,
+                                                        int chunk,
                                                         const int* __restrict__ ctr, const int* __restrict__ aux,
                                                         int* __restrict__ recbase, int* __restrict__ cells,
                                                         int* __restrict__ slot0, int* __restrict__ meta,
@@ -132,8 +133,10 @@ __global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ 
   const int mask = corner_mask(v, r, tri != 0);
   if (n > lm) {
     const int slot = aux[(long long)b * t + v];
-    if (slot < hcap)
-      ((int4*)heavy)[(long long)b * hcap + slot] = make_int4(v, recbase[(long long)b * t + v], n, mask);
+    const int rb = recbase[(long long)b * t + v];
+    for (int k = 0, o = 0; o < n; ++k, o += chunk)
+      if (slot + k < hcap)
+        ((int4*)heavy)[(long long)b * hcap + slot + k] = make_int4(v, rb + o, min(chunk, n - o), mask);
     return;
   }
   int j = lm - n;
@@ -228,7 +231,8 @@ __device__ __forceinline__ int cell_local(int v) { return (((v >> 5) / kCl) << 5
 template <bool TRI>
 __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
     cp_cluster_kernel(const int* __restrict__ vox_coords, const float* __restrict__ fcoords, int r,
-                      int* __restrict__ ind_out, int n, int t, int tq, int lm, int* __restrict__ cnt_out,
+                      int* __restrict__ ind_out, int n, int t, int tq, int lm, int chunk,
+                      int* __restrict__ cnt_out,
                       int* __restrict__ rank, int* __restrict__ cells, int* __restrict__ slot0,
                       int* __restrict__ meta, int* __restrict__ heavy, void* __restrict__ rec, int lcap, int hcap,
                       int rcap) {
@@ -246,8 +250,8 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
   const float* fb = TRI ? fcoords + base * 3 : nullptr;
   const int* vb = TRI ? nullptr : vox_coords + base * 3;
   const int r2 = r * r;
-  const int chunk = (n + kCl - 1) / kCl;
-  const int i_lo = min(n, q * chunk), i_hi = min(n, i_lo + chunk);  // this CTA's points
+  const int ppc = (n + kCl - 1) / kCl;
+  const int i_lo = min(n, q * ppc), i_hi = min(n, i_lo + ppc);  // this CTA's points
   for (int i = tid; i < tq; i += nt) tab[i] = 0;
   if (tid < kNB) { bin[tid] = 0; pos[tid] = 0; }
   cluster.sync();
@@ -299,7 +303,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
     if (v >= t) continue;
     const int c = tab[l];
     if (cnt_out) cnt_out[(long long)b * t + v] = c;
-    if (c > 0) atomicAdd(bin + (c <= lm ? c : kH), 1);
+    if (c > 0) atomicAdd(bin + (c <= lm ? c : kH), c <= lm ? 1 : ((c - 1) / chunk + 1));
     if (c > lm) atomicAdd(bin + kHP, c);
   }
   cluster.sync();
@@ -354,10 +358,13 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
         slot0[(long long)b * lcap + si] = (corner_mask(v, r, TRI) << 24) | s0;
       }
     } else if (c > lm) {
-      const int slot = off[kH] + atomicAdd(pos + kH, 1);
+      const int slot = off[kH] + atomicAdd(pos + kH, ((c - 1) / chunk + 1));
       const int rb = off[kHP] + atomicAdd(pos + kHP, c);
       tab[l] = rb;
-      if (slot < hcap) ((int4*)heavy)[(long long)b * hcap + slot] = make_int4(v, rb, c, corner_mask(v, r, TRI));
+      const int mask = corner_mask(v, r, TRI);
+      for (int k = 0, o = 0; o < c; ++k, o += chunk)
+        if (slot + k < hcap)
+          ((int4*)heavy)[(long long)b * hcap + slot + k] = make_int4(v, rb + o, min(chunk, c - o), mask);
     }
   }
   if (q == 0)
@@ -407,7 +414,7 @@ static long long lcap_of(long long n, long long t) { return (((n < t ? n : t) + 
 
 size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear) {
   size_t s = 0;
-  const long long lcap = lcap_of(n, t), hcap = n / (kLightMaxMean + 1) + 1, rcap = n + kEllPad;
+  const long long lcap = lcap_of(n, t), hcap = n / (kLightMaxMean + 1) + n / kHeavyChunk + 2, rcap = n + kEllPad;
   s += align256((size_t)b * lcap * 4) * 2 + align256((size_t)b * kCtr * 4);  // cells (+counters), slot0
   s += align256((size_t)b * kMetaInts * 4);                    // meta
   s += align256((size_t)b * hcap * 4 * 4);                     // heavy
@@ -423,7 +430,8 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
   const bool tri = float_coords != nullptr;
   plan->lcap = (int)lcap_of(n, t);
   plan->light_max = tri ? kLightMaxTri : kLightMaxMean;
-  plan->hcap = n / (plan->light_max + 1) + 1;
+  plan->chunk = tri ? kHeavyChunk : 0x7fffffff;  // mean plans: the consumer stores a cell's mean, no pieces
+  plan->hcap = n / (plan->light_max + 1) + (tri ? n / kHeavyChunk : 0) + 2;
   plan->rcap = n + kEllPad;
   // cells and the counters are zeroed by ONE memset: they are carved from one block
   const size_t zero_ints = (size_t)b * plan->lcap + (size_t)b * kCtr;
@@ -452,11 +460,11 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
     }
     if (tri)
       cp_cluster_kernel<true><<<b * kCl, kPlanThreads, tab_bytes, st>>>(
-          nullptr, float_coords, r, nullptr, n, t, tq, plan->light_max, nullptr, rank, plan->cells, plan->slot0,
+          nullptr, float_coords, r, nullptr, n, t, tq, plan->light_max, plan->chunk, nullptr, rank, plan->cells, plan->slot0,
           plan->meta, plan->heavy, plan->rec, plan->lcap, plan->hcap, plan->rcap);
     else
       cp_cluster_kernel<false><<<b * kCl, kPlanThreads, tab_bytes, st>>>(
-          vox_coords, nullptr, r, ind_out, n, t, tq, plan->light_max, cnt, rank, plan->cells, plan->slot0,
+          vox_coords, nullptr, r, ind_out, n, t, tq, plan->light_max, plan->chunk, cnt, rank, plan->cells, plan->slot0,
           plan->meta, plan->heavy, plan->rec, plan->lcap, plan->hcap, plan->rcap);
     PCFM_LAUNCHED();
     return 0;
@@ -469,9 +477,9 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
     else cp_count_kernel<false><<<gp, 256, 0, st>>>(vox_coords, nullptr, r, ind_out, n, t, cnt, rank);
     PCFM_LAUNCHED();
   }
-  cp_classify_kernel<<<gt, 256, 0, st>>>(cnt, t, plan->light_max, ctr, aux, recbase);
+  cp_classify_kernel<<<gt, 256, 0, st>>>(cnt, t, plan->light_max, plan->chunk, ctr, aux, recbase);
   PCFM_LAUNCHED();
-  cp_layout_kernel<<<gt, 256, 0, st>>>(cnt, t, r, tri ? 1 : 0, plan->light_max, ctr, aux, recbase, plan->cells, plan->slot0, plan->meta,
+  cp_layout_kernel<<<gt, 256, 0, st>>>(cnt, t, r, tri ? 1 : 0, plan->light_max, plan->chunk, ctr, aux, recbase, plan->cells, plan->slot0, plan->meta,
                                        plan->heavy, plan->lcap, plan->hcap);
   PCFM_LAUNCHED();
   if (n > 0) {

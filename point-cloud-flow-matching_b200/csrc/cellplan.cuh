@@ -20,6 +20,8 @@ namespace pcfm {
 constexpr int kLightCap = 64;      // upper bound of light_max (<= 255: 8-bit count field of CellPlan::cells)
 constexpr int kLightMaxMean = 32;
 constexpr int kLightMaxTri = 64;
+constexpr int kHeavyChunk = 256;   // trilinear plans: a heavy cell is listed as pieces of at most this many records, so no
+                                  // single warp owns a 2000-point cell (the pieces are combined with atomics anyway)
 constexpr int kSortMax = 16;   // light cells up to this size keep their records in ascending point order
 constexpr int kMetaInts = 4;   // per batch element: [0] end of the light list (multiple of 32), [1] heavy cells
 
@@ -27,9 +29,10 @@ struct CellPlan {
   int* cells = nullptr;    // [B, lcap]  light cells, count-descending: (count << 24) | cell; 0 = hole
   int* slot0 = nullptr;    // [B, lcap]  (corner mask << 24) | first record slot (records are 32 slots apart)
   int* meta = nullptr;     // [B, kMetaInts]
-  int* heavy = nullptr;    // [B, hcap, 4]  {cell, first slot, count, corner mask}
+  int* heavy = nullptr;    // [B, hcap, 4]  {cell, first slot, count, corner mask} per heavy cell (mean plans) or per
+                           //               piece of <= kHeavyChunk records of a heavy cell (trilinear plans)
   void* rec = nullptr;     // [B, rcap] records
-  int lcap = 0, hcap = 0, rcap = 0, light_max = 0;
+  int lcap = 0, hcap = 0, rcap = 0, light_max = 0, chunk = 0;
 };
 
 struct TriRec {  // 16-byte record of a trilinear plan
