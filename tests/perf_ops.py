@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--ops", default="")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--opt", default="", help="extra pcfm_set_option pairs, e.g. devox_rep=0,stage=1")
     ap.add_argument("--plan", type=int, default=0, help="pcfm_set_option('plan', .): 1 = multi-kernel cell-plan build")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: r x N x C sweep (B=2)")
     args = ap.parse_args()
@@ -46,6 +47,8 @@ def main():
         ref = {k: build_ref.load_ref(k) for k in ("pvcnn", "chamfer", "emd")}
     dev = "cuda"
     _lib.set_option("plan", args.plan)
+    for kv in filter(None, args.opt.split(",")):
+        _lib.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     g = torch.Generator(device=dev).manual_seed(0)
     B, N = 8, 20000
     rows = []
