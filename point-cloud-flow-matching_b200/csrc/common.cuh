@@ -18,6 +18,7 @@ extern int64_t g_launches;      // kernels launched by this library (pcfm_launch
 extern int g_opt_devox_bwd;     // see pcfm_set_option
 extern int g_opt_vox_fwd;
 extern int g_opt_stage;
+extern int g_opt_devox_il;      // 1 = channel-interleaved planes in devoxelize forward when G >= 4 (default)
 extern int g_opt_plan;          // 0 = fused cell-plan build when it fits, 1 = always the multi-kernel build
 extern int g_num_sms;           // cached SM count of the current device (148 on B200)
 int num_sms();

@@ -150,7 +150,9 @@ DEVOX_SHAPES = [
     dict(seed=15, b=1, c=5, n=7, res=2),
     dict(seed=18, b=2, c=304, n=3001, res=8),     # enough rows for the two-channels-per-CTA backward (unaligned rows)
     dict(seed=19, b=2, c=300, n=6000, res=16),    # same, 16-byte aligned rows (TMA staging)
-    dict(seed=20, b=2, c=608, n=1000, res=8),     # four channels per CTA at r=8: replicated-plane forward kernel
+    dict(seed=20, b=2, c=608, n=1000, res=8),     # four channels per CTA: channel-interleaved forward kernel <4,8>
+    dict(seed=21, b=2, c=592, n=1500, res=16),    # <4,16>
+    dict(seed=22, b=2, c=592, n=700, res=12),     # <4,runtime r>
 ]
 
 
