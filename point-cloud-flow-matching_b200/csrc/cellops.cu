@@ -28,12 +28,16 @@ __global__ void __launch_bounds__(1024, 2)
                         int hcap, int rcap, int use_tma) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
+  __shared__ int next_item;
   const int c = blockIdx.x, b = blockIdx.y;
   const float* row_g = feat + ((long long)b * C + c) * N;
   float* o = out + ((long long)b * C + c) * T;
-  if (ROW_SMEM && threadIdx.x == 0) {
-    mbar_init(&bar, 1);
-    fence_mbar_init();
+  if (threadIdx.x == 0) {
+    next_item = 0;
+    if (ROW_SMEM) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
   }
   __syncthreads();
   // issue the row copy, then zero the output row while it is in flight
@@ -59,47 +63,53 @@ __global__ void __launch_bounds__(1024, 2)
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
   const int* rc = rec + (long long)b * rcap;
-  const int nl = meta[b * kMetaInts + 0];
-  for (int ci = threadIdx.x; ci < nl; ci += blockDim.x) {
-    const int d = cl[ci];
-    const int n = (int)((unsigned)d >> 24), t = d & 0xffffff;
-    if (n == 0) continue;  // alignment hole
-    const int s0 = sl[ci] & 0xffffff;
-    const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
-    float acc = 0.f;
-    for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread, branch-free tail:
-      int p[4];                          // a padded slot re-reads the last record and contributes an exact +0
-#pragma unroll
-      for (int k = 0; k < 4; ++k) p[k] = rc[s0 + 32 * min(i0 + k, n - 1)];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
-        f = (i0 + k < n) ? f : 0.f;
-        acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
-      }
-    }
-    o[t] = acc;
-  }
-  const int nh = meta[b * kMetaInts + 1];
+  const int nslice = meta[b * kMetaInts + 0] >> 5, nitem = nslice + meta[b * kMetaInts + 1];
   const int lane = threadIdx.x & 31;
-  for (int h = threadIdx.x >> 5; h < nh; h += blockDim.x >> 5) {
-    const int4 hd = ((const int4*)heavy)[(long long)b * hcap + h];
-    const int t = hd.x, s0 = hd.y, n = hd.z;
-    const float rcp = __frcp_rn((float)n);
-    float acc = 0.f;
-    for (int i = lane; i < n; i += 32 * PCFM_HEAVY_U) {  // PCFM_HEAVY_U independent record loads in flight per lane
-      int p[PCFM_HEAVY_U];
+  // work items taken by whole warps from a shared counter: slices of 32 light cells (longest first), then heavy cells
+  for (;;) {
+    int item = 0;
+    if (lane == 0) item = atomicAdd(&next_item, 1);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= nitem) break;
+    if (item < nslice) {
+      const int ci = (item << 5) | lane;
+      const int d = cl[ci];
+      const int n = (int)((unsigned)d >> 24), t = d & 0xffffff;
+      if (n == 0) continue;  // alignment hole (no warp-level operation below)
+      const int s0 = sl[ci] & 0xffffff;
+      const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
+      float acc = 0.f;
+      for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread, branch-free tail:
+        int p[4];                          // a padded slot re-reads the last record and contributes an exact +0
 #pragma unroll
-      for (int k = 0; k < PCFM_HEAVY_U; ++k) p[k] = rc[s0 + min(i + 32 * k, n - 1)];
+        for (int k = 0; k < 4; ++k) p[k] = rc[s0 + 32 * min(i0 + k, n - 1)];
 #pragma unroll
-      for (int k = 0; k < PCFM_HEAVY_U; ++k) {
-        float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
-        f = (i + 32 * k < n) ? f : 0.f;  // a padded slot contributes an exact +0
-        acc = __fadd_rn(acc, __fmul_rn(f, rcp));
+        for (int k = 0; k < 4; ++k) {
+          float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
+          f = (i0 + k < n) ? f : 0.f;
+          acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
+        }
       }
+      o[t] = acc;
+    } else {
+      const int4 hd = ((const int4*)heavy)[(long long)b * hcap + (item - nslice)];
+      const int t = hd.x, s0 = hd.y, n = hd.z;
+      const float rcp = __frcp_rn((float)n);
+      float acc = 0.f;
+      for (int i = lane; i < n; i += 32 * PCFM_HEAVY_U) {  // PCFM_HEAVY_U independent record loads in flight per lane
+        int p[PCFM_HEAVY_U];
+#pragma unroll
+        for (int k = 0; k < PCFM_HEAVY_U; ++k) p[k] = rc[s0 + min(i + 32 * k, n - 1)];
+#pragma unroll
+        for (int k = 0; k < PCFM_HEAVY_U; ++k) {
+          float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
+          f = (i + 32 * k < n) ? f : 0.f;  // a padded slot contributes an exact +0
+          acc = __fadd_rn(acc, __fmul_rn(f, rcp));
+        }
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) o[t] = acc;
     }
-    acc = warp_sum(acc);
-    if (lane == 0) o[t] = acc;
   }
 }
 

@@ -16,9 +16,9 @@ namespace pcfm {
 
 // Cells longer than the plan's `light_max` are reduced by a whole warp.  Thread-per-cell costs about one instruction
 // slot per point-lane but serialises a cell; warp-per-cell adds ~100 warp instructions per cell.  Measured on B200
-// (N=20000, r=8..32): 32 is best for mean plans (1 FMA per point), 64 for trilinear plans (~25 per point).
+// (N=20000, r=8..32, warps taking work items dynamically): 64 beats 16, 32 and 128 for both plan kinds.
 constexpr int kLightCap = 64;      // upper bound of light_max (<= 255: 8-bit count field of CellPlan::cells)
-constexpr int kLightMaxMean = 32;
+constexpr int kLightMaxMean = 64;
 constexpr int kLightMaxTri = 64;
 constexpr int kHeavyChunk = 256;   // trilinear plans: a heavy cell is listed as pieces of at most this many records, so no
                                   // single warp owns a 2000-point cell (the pieces are combined with atomics anyway)
