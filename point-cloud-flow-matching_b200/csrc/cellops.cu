@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(1024, 2)
     for (int i = bulk + threadIdx.x; i < N; i += blockDim.x) smem[i] = __ldg(row_g + i);
     if (bulk > 0) mbar_wait(&bar, 0);
   }
+  griddep_wait();   // everything above is independent of the plan (PDL: overlaps the plan kernel)
   __syncthreads();  // row visible; zero stores ordered before the sums below (same CTA)
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
@@ -167,6 +168,7 @@ __global__ void __launch_bounds__(1024, 1)
     for (int i = bulk + threadIdx.x; i < N; i += blockDim.x) row[i] = __ldg(row_g + i);
     if (bulk > 0) mbar_wait(&bar, 0);
   }
+  griddep_wait();  // everything above is independent of the plan (PDL: overlaps the plan kernel)
   __syncthreads();
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
@@ -342,13 +344,13 @@ int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, i
     attr_set = true;
   }
   if (n <= kMaxStageFloats)
-    vox_fwd_cell_kernel<true><<<grid, 1024, (size_t)n * sizeof(float), st>>>(
-        features, plan.cells, plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c, n, t, plan.lcap,
-        plan.hcap, plan.rcap, g_opt_stage == 0);
+    PCFM_CUDA(launch_dependent(vox_fwd_cell_kernel<true>, grid, dim3(1024), (size_t)n * sizeof(float), st, plan.pdl,
+                               features, plan.cells, plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c,
+                               n, t, plan.lcap, plan.hcap, plan.rcap, (int)(g_opt_stage == 0)));
   else
-    vox_fwd_cell_kernel<false><<<grid, 1024, 0, st>>>(features, plan.cells, plan.slot0, plan.meta, plan.heavy,
-                                                      (const int*)plan.rec, out, c, n, t, plan.lcap, plan.hcap,
-                                                      plan.rcap, 0);
+    PCFM_CUDA(launch_dependent(vox_fwd_cell_kernel<false>, grid, dim3(1024), 0, st, plan.pdl, features, plan.cells,
+                               plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c, n, t, plan.lcap,
+                               plan.hcap, plan.rcap, 0));
   PCFM_LAUNCHED();
   return 0;
 }
@@ -390,13 +392,15 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
   // small planes (r <= 16): two CTAs of 512 threads per SM overlap one CTA's staging with the other's compute
   const int threads = (row_smem && devox_bwd_smem(n, r, true) <= 110 * 1024) ? 512 : 1024;
   if (row_smem)
-    devox_bwd_cell_kernel<true><<<grid, threads, devox_bwd_smem(n, r, true), st>>>(
-        grad_y, plan.cells, plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec, grad_x, c, n, r, plan.lcap,
-        plan.hcap, plan.rcap, g_opt_stage == 0);
+    PCFM_CUDA(launch_dependent(devox_bwd_cell_kernel<true>, grid, dim3(threads), devox_bwd_smem(n, r, true), st,
+                               plan.pdl, grad_y, plan.cells, plan.slot0, plan.meta, plan.heavy,
+                               (const float4*)plan.rec, grad_x, c, n, r, plan.lcap, plan.hcap, plan.rcap,
+                               (int)(g_opt_stage == 0)));
   else
-    devox_bwd_cell_kernel<false><<<grid, threads, devox_bwd_smem(n, r, false), st>>>(
-        grad_y, plan.cells, plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec, grad_x, c, n, r, plan.lcap,
-        plan.hcap, plan.rcap, g_opt_stage == 0);
+    PCFM_CUDA(launch_dependent(devox_bwd_cell_kernel<false>, grid, dim3(threads), devox_bwd_smem(n, r, false), st,
+                               plan.pdl, grad_y, plan.cells, plan.slot0, plan.meta, plan.heavy,
+                               (const float4*)plan.rec, grad_x, c, n, r, plan.lcap, plan.hcap, plan.rcap,
+                               (int)(g_opt_stage == 0)));
   PCFM_LAUNCHED();
   return 0;
 }

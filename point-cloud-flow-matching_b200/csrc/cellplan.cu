@@ -236,6 +236,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
                       int* __restrict__ rank, int* __restrict__ cells, int* __restrict__ slot0,
                       int* __restrict__ meta, int* __restrict__ heavy, void* __restrict__ rec, int lcap, int hcap,
                       int rcap) {
+  griddep_launch_dependents();  // the consumer kernel may start staging its rows now; it waits before reading the plan
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ int tab[];  // [tq] this CTA's share of the per-cell table
   __shared__ int bin[kNB];      // this CTA's histogram of cell sizes (read by the other CTAs in phase 3)
@@ -467,6 +468,7 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
           vox_coords, nullptr, r, ind_out, n, t, tq, plan->light_max, plan->chunk, cnt, rank, plan->cells, plan->slot0,
           plan->meta, plan->heavy, plan->rec, plan->lcap, plan->hcap, plan->rcap);
     PCFM_LAUNCHED();
+    plan->pdl = g_opt_pdl != 0;
     return 0;
   }
   PCFM_CUDA(cudaMemsetAsync(cnt, 0, (size_t)b * t * sizeof(int), st));

@@ -33,6 +33,7 @@ struct CellPlan {
                            //               piece of <= kHeavyChunk records of a heavy cell (trilinear plans)
   void* rec = nullptr;     // [B, rcap] records
   int lcap = 0, hcap = 0, rcap = 0, light_max = 0, chunk = 0;
+  bool pdl = false;        // built by the fused kernel, which releases dependent launches early (launch_dependent)
 };
 
 struct TriRec {  // 16-byte record of a trilinear plan

@@ -19,6 +19,7 @@ extern int g_opt_devox_bwd;     // see pcfm_set_option
 extern int g_opt_vox_fwd;
 extern int g_opt_stage;
 extern int g_opt_devox_il;      // 1 = channel-interleaved planes in devoxelize forward when G >= 4 (default)
+extern int g_opt_pdl;           // 1 = row kernels overlap the tail of the fused plan kernel (PDL), 0 = plain launches
 extern int g_opt_plan;          // 0 = fused cell-plan build when it fits, 1 = always the multi-kernel build
 extern int g_num_sms;           // cached SM count of the current device (148 on B200)
 int num_sms();
@@ -38,6 +39,24 @@ int num_sms();
 
 static inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// <<<grid, block, smem, st>>> launch that, when `dependent`, lets the kernel overlap the tail of the previous kernel on
+// the stream (see griddep_wait() below)
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_dependent(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                           bool dependent, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = dependent ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
 
 // bump allocator over the caller's workspace
 struct Workspace {
@@ -141,6 +160,13 @@ __device__ __forceinline__ void stage_floats(float* smem_dst, const float* gmem_
   if (bulk_count > 0) mbar_wait(bar, phase);
   __syncthreads();
 }
+
+// ---- programmatic dependent launch (PDL): a kernel launched with launch_dependent() may start while the previous
+// kernel on the stream is still running once that kernel has called griddep_launch_dependents(); it must call
+// griddep_wait() before touching anything the previous kernel writes (the wait returns when that grid has completed
+// and its memory is visible).  Both are no-ops for kernels launched normally.
+__device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
