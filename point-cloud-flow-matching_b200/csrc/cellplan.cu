@@ -257,26 +257,26 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
   if (tid < kNB) { bin[tid] = 0; pos[tid] = 0; }
   cluster.sync();
   // ---- 1. count: cell key of every point, its rank inside the cell ----
+  // `single`: every thread sees each of its points once (at most kPlanUnroll of them), so key / rank / fractions stay
+  // in registers until phase 5 instead of a round trip through global memory
+  const bool single = ppc <= nt * kPlanUnroll;
+  int key[kPlanUnroll], rk[kPlanUnroll];
+  float fx[kPlanUnroll], fy[kPlanUnroll], fz[kPlanUnroll];
   for (int i0 = i_lo; i0 < i_hi; i0 += nt * kPlanUnroll) {
-    int key[kPlanUnroll];
 #pragma unroll
     for (int u = 0; u < kPlanUnroll; ++u) {
       const int i = i0 + u * nt + tid;
       key[u] = -1;
       if (i < i_hi) {
-        if (TRI) {
-          float fx, fy, fz;
-          key[u] = floor_cell(fb, i, n, r, &fx, &fy, &fz);
-        } else {
-          key[u] = vb[i] * r2 + vb[(long long)i + n] * r + vb[(long long)i + 2LL * n];  // vox.cu:31
-        }
+        if (TRI) key[u] = floor_cell(fb, i, n, r, &fx[u], &fy[u], &fz[u]);
+        else key[u] = vb[i] * r2 + vb[(long long)i + n] * r + vb[(long long)i + 2LL * n];  // vox.cu:31
       }
     }
 #pragma unroll
     for (int u = 0; u < kPlanUnroll; ++u) {
       const int i = i0 + u * nt + tid;
       const bool valid = i < i_hi && key[u] >= 0 && key[u] < t;
-      int rk = -1;
+      rk[u] = -1;
 #if PCFM_PLAN_AGG
       // lanes of a warp that hit the same cell share one DSMEM atomic (dense clouds: most of a warp at r = 8)
       const unsigned act = __ballot_sync(0xffffffffu, valid);
@@ -286,13 +286,13 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
         int old = 0;
         if (lane == leader)
           old = atomicAdd(cluster.map_shared_rank(tab, cell_owner(key[u])) + cell_local(key[u]), __popc(peers));
-        rk = __shfl_sync(peers, old, leader) + __popc(peers & ((1u << lane) - 1u));
+        rk[u] = __shfl_sync(peers, old, leader) + __popc(peers & ((1u << lane) - 1u));
       }
 #else
-      if (valid) rk = atomicAdd(cluster.map_shared_rank(tab, cell_owner(key[u])) + cell_local(key[u]), 1);
+      if (valid) rk[u] = atomicAdd(cluster.map_shared_rank(tab, cell_owner(key[u])) + cell_local(key[u]), 1);
 #endif
       if (i < i_hi) {
-        rank[base + i] = rk;
+        if (!single) rank[base + i] = rk[u];
         if (!TRI) ind_out[base + i] = key[u];
       }
     }
@@ -373,16 +373,16 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
   cluster.sync();
   // ---- 5. fill the records of this CTA's points ----
   for (int i0 = i_lo; i0 < i_hi; i0 += nt * kPlanUnroll) {
-    int rk[kPlanUnroll], key[kPlanUnroll];
-    float fx[kPlanUnroll], fy[kPlanUnroll], fz[kPlanUnroll];
+    if (!single) {
 #pragma unroll
-    for (int u = 0; u < kPlanUnroll; ++u) {
-      const int i = i0 + u * nt + tid;
-      rk[u] = -1;
-      if (i < i_hi) {
-        rk[u] = rank[base + i];
-        if (TRI) key[u] = floor_cell(fb, i, n, r, &fx[u], &fy[u], &fz[u]);
-        else key[u] = ind_out[base + i];
+      for (int u = 0; u < kPlanUnroll; ++u) {
+        const int i = i0 + u * nt + tid;
+        rk[u] = -1;
+        if (i < i_hi) {
+          rk[u] = rank[base + i];
+          if (TRI) key[u] = floor_cell(fb, i, n, r, &fx[u], &fy[u], &fz[u]);
+          else key[u] = ind_out[base + i];
+        }
       }
     }
 #pragma unroll
