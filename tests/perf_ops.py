@@ -36,6 +36,7 @@ def main():
     ap.add_argument("--ops", default="")
     ap.add_argument("--no-variants", action="store_true")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--warm", type=int, default=3, help="untimed calls before the timed ones (0 for ncu captures)")
     ap.add_argument("--opt", default="", help="extra pcfm_set_option pairs, e.g. devox_rep=0,stage=1")
     ap.add_argument("--plan", type=int, default=0, help="pcfm_set_option('plan', .): 1 = multi-kernel cell-plan build")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: r x N x C sweep (B=2)")
@@ -89,7 +90,7 @@ def main():
         if args.ops:
             ops = {k: v for k, v in ops.items() if k in args.ops.split(",")}
         for op, fn in ops.items():
-            ms = timeit(fn, iters=args.iters)
+            ms = timeit(fn, iters=args.iters, warm=args.warm)
             row = {"shape": name, "C": c, "r": r, "B": b, "N": n, "op": op, "ms": round(ms, 4),
                    "max_cnt": int(cnt.max()), "occupied": int((cnt > 0).sum())}
             if op in byt:
