@@ -1,6 +1,9 @@
 // pointops.cu — ball query, furthest point sampling, 3-nearest-neighbour search (+ interpolate forward).
 #include "rows.cuh"
 
+#include <cooperative_groups.h>
+namespace cg = cooperative_groups;
+
 namespace pcfm {
 
 // =================================================================================================
@@ -150,6 +153,119 @@ __global__ void __launch_bounds__(1024, 1)
   }
 }
 
+// -------------------------------------------------------------------------------------------------
+// Cluster version: one thread-block cluster of 8 CTAs per cloud, every point (x, y, z, running distance) lives in a
+// REGISTER of exactly one thread for all m rounds.  Per round: register update -> warp / CTA arg-max -> the winning
+// thread publishes (key, x, y, z) in its CTA's slot -> ONE cluster barrier -> every warp reads the 8 slots through
+// distributed shared memory and reduces them: the next centre's coordinates arrive with the winner, no extra
+// round trip.  Same 64-bit key => same winners as the one-CTA kernel and the reference.
+// -------------------------------------------------------------------------------------------------
+constexpr int kFpsCl = 8;
+struct __align__(16) FpsSlot {
+  unsigned long long key;
+  float x, y, z;
+  int pad;
+};
+
+// XYZ_SMEM (clouds of 65537..131072 points, 16 points per thread): the coordinates live in shared memory
+// ([3][points of this CTA], conflict-free strided reads), only the running distances stay in registers.
+template <int PPT, bool XYZ_SMEM>
+__global__ void __cluster_dims__(kFpsCl, 1, 1) __launch_bounds__(1024, 1)
+    fps_cluster_kernel(const float* __restrict__ coords, int n, int m, int* __restrict__ indices) {
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) float sxyz[];  // XYZ_SMEM: x[per] y[per] z[per]
+  __shared__ unsigned long long wbest[32];
+  __shared__ FpsSlot slot[2];
+  if (m <= 0) return;
+  const int q = (int)cluster.block_rank(), b = blockIdx.x / kFpsCl;
+  const float* cb = coords + (long long)b * 3 * n;
+  int* ib = indices + (long long)b * m;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, wid = tid >> 5, nw = nt >> 5;
+  const int per = (n + kFpsCl - 1) / kFpsCl, k_lo = min(n, q * per), k_hi = min(n, k_lo + per);
+  float px[XYZ_SMEM ? 1 : PPT], py[XYZ_SMEM ? 1 : PPT], pz[XYZ_SMEM ? 1 : PPT], pd[PPT];
+#pragma unroll
+  for (int i = 0; i < PPT; ++i) {
+    const int k = k_lo + tid + i * nt;
+    const bool v = k < k_hi;
+    const float x = v ? cb[k] : 0.f, y = v ? cb[(long long)n + k] : 0.f, z = v ? cb[2LL * n + k] : 0.f;
+    if (XYZ_SMEM) {
+      if (v) { sxyz[k - k_lo] = x; sxyz[per + k - k_lo] = y; sxyz[2 * per + k - k_lo] = z; }
+    } else {
+      px[i] = x; py[i] = y; pz[i] = z;
+    }
+    pd[i] = 1e38f;  // sampling.cpp:53
+  }
+  if (XYZ_SMEM) __syncthreads();
+  if (q == 0 && tid == 0) ib[0] = 0;
+  float x1 = cb[0], y1 = cb[n], z1 = cb[2LL * n];  // the first centre is point 0
+  for (int j = 1; j < m; ++j) {
+    unsigned long long best = 0ull;  // below every real key (distances are >= 0)
+    float bx = 0.f, by = 0.f, bz = 0.f;
+#pragma unroll
+    for (int i = 0; i < PPT; ++i) {
+      const int k = k_lo + tid + i * nt;
+      float x, y, z;
+      if (XYZ_SMEM) {
+        const int l = min(k, k_hi - 1) - k_lo;  // clamped: an idle slot re-reads a valid point, its key is 0
+        x = sxyz[l]; y = sxyz[per + l]; z = sxyz[2 * per + l];
+      } else {
+        x = px[i]; y = py[i]; z = pz[i];
+      }
+      const float d2 = fminf(sq3(x - x1, y - y1, z - z1), pd[i]);  // point - last selected
+      pd[i] = d2;
+      const unsigned long long key = k < k_hi ? fps_key(d2, k) : 0ull;
+      if (key > best) { best = key; bx = x; by = y; bz = z; }
+    }
+    unsigned long long v = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+      v = other > v ? other : v;
+    }
+    if (lane == 0) wbest[wid] = v;
+    __syncthreads();
+    v = lane < nw ? wbest[lane] : 0ull;  // every warp reduces the warp results itself: one barrier, no broadcast
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
+      v = other > v ? other : v;
+    }
+    FpsSlot* mine = &slot[j & 1];
+    if (v == 0ull) {
+      if (tid == 0) { mine->key = 0ull; mine->x = 0.f; mine->y = 0.f; mine->z = 0.f; }  // this CTA owns no point
+    } else if (best == v) {  // keys are unique per point: exactly one thread
+      mine->key = v; mine->x = bx; mine->y = by; mine->z = bz;
+    }
+    cluster.sync();
+    // lanes 0..7 of every warp fetch one CTA's slot each, 3 shuffle steps pick the cluster-wide winner
+    unsigned long long ck = 0ull;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    if (lane < kFpsCl) {
+      const FpsSlot* rs = cluster.map_shared_rank(mine, lane);
+      const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rs);            // key, (x, y)
+      const float2 zz = *reinterpret_cast<const float2*>(&rs->z);                // z, pad
+      ck = a.x;
+      cx = __uint_as_float((unsigned)a.y);
+      cy = __uint_as_float((unsigned)(a.y >> 32));
+      cz = zz.x;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, ck, o);
+      const float ox = __shfl_xor_sync(0xffffffffu, cx, o), oy = __shfl_xor_sync(0xffffffffu, cy, o),
+                  oz = __shfl_xor_sync(0xffffffffu, cz, o);
+      if (ok > ck) { ck = ok; cx = ox; cy = oy; cz = oz; }
+    }
+    ck = __shfl_sync(0xffffffffu, ck, 0);
+    x1 = __shfl_sync(0xffffffffu, cx, 0);
+    y1 = __shfl_sync(0xffffffffu, cy, 0);
+    z1 = __shfl_sync(0xffffffffu, cz, 0);
+    if (ck == 0ull) { x1 = cb[0]; y1 = cb[n]; z1 = cb[2LL * n]; }  // degenerate (all distances 0 at index 0): index 0
+    if (q == 0 && tid == 0) ib[j] = ck ? fps_key_index(ck) : 0;
+  }
+  cluster.sync();  // no CTA leaves while its slots may still be read
+}
+
 // =================================================================================================
 // three nearest neighbours (neighbor_interpolate.cu:20-75): one thread per point, centres streamed
 // through shared memory; strict-< insertion keeps the earliest centre on ties.
@@ -252,6 +368,34 @@ int pcfm_furthest_point_sampling(const float* coords, int b, int n, int m, int* 
   if (b == 0 || m == 0) return 0;
   if (!coords || !indices || n == 0) return PCFM_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
+  // Cluster kernel from 6144 points up (below, its ~1.4 us cluster barrier per round loses to the one-CTA kernel):
+  // points in registers (<= 8 per thread) up to 65536 points, coordinates in shared memory up to 131072.
+  if (g_opt_fps == 0 && n >= 6144 && n <= kFpsCl * 1024 * 16) {
+    const int per = cdiv(n, kFpsCl);
+    dim3 grid(b * kFpsCl);
+    if (per > 1024 * 8) {
+      static bool attr_set = false;
+      const size_t smem = (size_t)per * 3 * sizeof(float);
+      if (!attr_set) {
+        PCFM_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       16384 * 3 * (int)sizeof(float)));
+        attr_set = true;
+      }
+      fps_cluster_kernel<16, true><<<grid, 1024, smem, st>>>(coords, n, m, indices);
+    } else {
+      int nt = 512, ppt = 1;
+      while (ppt < 8 && nt * ppt < per) ppt *= 2;
+      if (nt * ppt < per) nt = 1024;
+      switch (ppt) {
+        case 1: fps_cluster_kernel<1, false><<<grid, nt, 0, st>>>(coords, n, m, indices); break;
+        case 2: fps_cluster_kernel<2, false><<<grid, nt, 0, st>>>(coords, n, m, indices); break;
+        case 4: fps_cluster_kernel<4, false><<<grid, nt, 0, st>>>(coords, n, m, indices); break;
+        default: fps_cluster_kernel<8, false><<<grid, nt, 0, st>>>(coords, n, m, indices); break;
+      }
+    }
+    PCFM_LAUNCHED();
+    return 0;
+  }
   const size_t smem = (size_t)n * 4 * sizeof(float);
   if (smem <= (size_t)kMaxStageFloats * sizeof(float)) {
     static bool attr_set = false;

@@ -119,6 +119,47 @@ def main():
             print(json.dumps(row), flush=True)
     if args.sweep:
         only = {"none"}
+    if only and "pointnet" in only:
+        # SURVEY 8(a) rows a8-a11 at the config-5 sizes: N points, M = N/4 centres (FPS), U = 32 neighbours, C = 64
+        for (b, n, c) in [(8, 4096, 64), (8, 20000, 64), (2, 100000, 64)]:
+            m, u = n // 4, 32
+            pts = torch.rand(b, 3, n, device=dev, generator=g) * 2 - 1
+            feat = torch.randn(b, c, n, device=dev, generator=g)
+            P = be.pvcnn
+            R = ref["pvcnn"] if ref else None
+            idx = P.furthest_point_sampling(pts, m)
+            ctr = P.gather_features_forward(pts, idx)
+            radius = 0.1 * 2.0
+            nb = P.ball_query(ctr, pts, radius, u)
+            grp = P.grouping_forward(feat, nb)
+            cfeat = torch.randn(b, c, m, device=dev, generator=g)
+            _, i3, w3 = P.three_nearest_neighbors_interpolate_forward(pts, ctr, cfeat)
+            gint = torch.randn(b, c, n, device=dev, generator=g)
+            cases = {
+                "fps": (lambda: P.furthest_point_sampling(pts, m), (lambda: R.furthest_point_sampling(pts, m)) if R else None),
+                "ball_query": (lambda: P.ball_query(ctr, pts, radius, u), (lambda: R.ball_query(ctr, pts, radius, u)) if R else None),
+                "grouping_fwd": (lambda: P.grouping_forward(feat, nb), (lambda: R.grouping_forward(feat, nb)) if R else None),
+                "grouping_bwd": (lambda: P.grouping_backward(grp, nb, n), (lambda: R.grouping_backward(grp, nb, n)) if R else None),
+                "gather_fwd": (lambda: P.gather_features_forward(feat, idx), (lambda: R.gather_features_forward(feat, idx)) if R else None),
+                "gather_bwd": (lambda: P.gather_features_backward(cfeat, idx, n), (lambda: R.gather_features_backward(cfeat, idx, n)) if R else None),
+                "three_nn_fwd": (lambda: P.three_nearest_neighbors_interpolate_forward(pts, ctr, cfeat),
+                                 (lambda: R.three_nearest_neighbors_interpolate_forward(pts, ctr, cfeat)) if R else None),
+                "three_nn_bwd": (lambda: P.three_nearest_neighbors_interpolate_backward(gint, i3, w3, m),
+                                 (lambda: R.three_nearest_neighbors_interpolate_backward(gint, i3, w3, m)) if R else None),
+            }
+            for op, (fn, rfn) in cases.items():
+                it = 2 if op == "fps" else args.iters
+                row = {"op": op, "B": b, "N": n, "M": m, "U": u, "C": c, "ms": round(timeit(fn, iters=it, warm=1), 4)}
+                if op == "fps":
+                    row["rounds_per_s"] = round(b * m / row["ms"] * 1e3)
+                if op == "ball_query":
+                    row["neighbours_found_mean"] = round(float((nb != nb[..., :1]).float().sum(-1).mean()) + 1, 2)
+                    row["Gevals_per_s_worst_case"] = round(b * m * n / row["ms"] / 1e6, 1)
+                if op == "three_nn_fwd":
+                    row["Gevals_per_s"] = round(b * m * n / row["ms"] / 1e6, 1)
+                if rfn is not None:
+                    row["ms_reference_cuda"] = round(timeit(rfn, iters=2, warm=1), 3)
+                rows.append(row); print(json.dumps(row), flush=True)
     if not only or "chamfer" in only:
         for (b, n, m) in [(32, 2000, 1000), (2, 2048, 2048), (8, 20000, 20000)]:
             a = torch.rand(b, n, 3, device=dev, generator=g); c2 = torch.rand(b, m, 3, device=dev, generator=g)
@@ -141,6 +182,8 @@ def main():
             rows.append(row); print(json.dumps(row), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     tag = "sweep_" + args.kind if args.sweep else args.kind
+    if args.only and not args.sweep:
+        tag += "_" + args.only.replace(",", "-")
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", f"perf_ops_{tag}.json"), "w"), indent=1)
 
 

@@ -217,6 +217,23 @@ PN_SHAPES = [
 ]
 
 
+@pytest.mark.parametrize("n,m,kind", [(600, 150, "lattice"), (3000, 700, "rand"), (9, 9, "rand"), (6144, 300, "lattice"),
+                                      (40000, 64, "rand"), (70000, 40, "rand"), (131073, 12, "rand")])
+def test_fps_cluster_and_single_cta_kernels_pick_the_reference_winners(be, oracle, n, m, kind):
+    """All FPS kernels (one CTA per cloud below 6144 and above 131072 points; 8-CTA cluster with the points in registers
+    up to 65536 points, coordinates in shared memory up to 131072) must reproduce the reference's choice in every
+    round, including its tie-break on lattice clouds."""
+    from pcfm import _lib
+    pts, _, _ = cases.pointnet_case(seed=45 + n % 7, b=2, c=1, n=n, m=m, kind=kind)
+    want = oracle.furthest_point_sampling(pts, m)
+    assert_equal(host(be.pvcnn.furthest_point_sampling(cu(pts), m)), want, "fps (default kernel)")
+    _lib.set_option("fps", 1)
+    try:
+        assert_equal(host(be.pvcnn.furthest_point_sampling(cu(pts), m)), want, "fps (one CTA per cloud)")
+    finally:
+        _lib.set_option("fps", 0)
+
+
 @pytest.mark.parametrize("kw", PN_SHAPES, ids=lambda k: f"{k['kind']}n{k['n']}m{k['m']}")
 def test_fps_ballquery_grouping_gather_3nn(be, oracle, ref, kw):
     pts, feat, cfeat = cases.pointnet_case(**kw)
