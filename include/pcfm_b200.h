@@ -192,6 +192,17 @@ int pcfm_emd_matchcost_backward(const float* grad_cost, const float* xyz1, const
  * defined as the reference operator applied to the pair (S[i], R[j]) — SURVEY.md section 8(e)).
  * ---------------------------------------------------------------------------------------------- */
 
+/* Chamfer distance for D-dimensional points, D in {2, 5, 6} (ChamferDistancePytorch/chamfer{2D,5D,6D}:
+ * chamfer6D.cu:11-183 forward, :185-237 backward; same contract as the 3-D entries above): xyz1 f32[B,N,D],
+ * xyz2 f32[B,M,D] -> dist1 f32[B,N], dist2 f32[B,M] (squared), idx1 i32[B,N], idx2 i32[B,M]; ties -> lowest index.
+ * Squared distance in the reference's contracted order (FMUL(d1,d1); FFMA(d0,d0,.); FFMA(d2,d2,.) ...).
+ * backward accumulates into caller-zeroed gradxyz1 f32[B,N,D], gradxyz2 f32[B,M,D]. */
+int pcfm_chamfer_nd_forward(const float* xyz1, const float* xyz2, int b, int n, int m, int d, float* dist1,
+                            float* dist2, int* idx1, int* idx2, pcfm_stream_t stream);
+int pcfm_chamfer_nd_backward(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,
+                             const int* idx1, const int* idx2, int b, int n, int m, int d, float* gradxyz1,
+                             float* gradxyz2, pcfm_stream_t stream);
+
 /* cd[i,j] = mean_k dist1(S_i,R_j)[k] + mean_l dist2(S_i,R_j)[l]  with dist1/dist2 as pcfm_chamfer3d_forward.
  * S f32[ns,N,3], R f32[nr,M,3] -> cd f32[ns,nr].  Each distance is evaluated once and feeds both minima. */
 int pcfm_chamfer3d_allpairs(const float* s, const float* r, int ns, int nr, int n, int m, float* cd,

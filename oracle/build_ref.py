@@ -1,12 +1,13 @@
 """Build the UNMODIFIED reference CUDA extensions into oracle/_ref/ (test infrastructure only).
 
-The reference's hot path is three pybind11/ATen CUDA extensions.  They are compiled here from the
+The reference's hot path is three pybind11/ATen CUDA extensions (plus chamfer_6D, a "next" row of SURVEY 8f).  They are compiled here from the
 sources where they lie under /root/reference (nothing is copied into this repo) with torch's
 cpp_extension builder for sm_100a, outputs only under oracle/_ref/ (git-ignored, shipped by gpurun):
 
   oracle/_ref/pvcnn/_pvcnn_backend.so   <- third_party/pvcnn/modules/functional/src/**   (backend.py:6-23)
   oracle/_ref/chamfer/chamfer_3D.so     <- third_party/ChamferDistancePytorch/chamfer3D/ (dist_chamfer_3D.py:12-16)
   oracle/_ref/emd/emd_ext.so            <- third_party/PyTorchEMD/cuda/                  (backend.py:11-26)
+  oracle/_ref/chamfer6d/chamfer_6D.so   <- third_party/ChamferDistancePytorch/chamfer6D/ (dist_chamfer_6D.py:16-21)
 
 Flags mirror the reference loaders (pvcnn: -O3 host only; chamfer: defaults; EMD: -O3 --use_fast_math).
 Only tests/, __graft_entry__.smoke() and tests/perf scripts may load these; the product never does.
@@ -48,6 +49,11 @@ def build(which=None):
         name="chamfer_3D",
         sources=[os.path.join(ch, "chamfer_cuda.cpp"), os.path.join(ch, "chamfer3D.cu")],
     )
+    c6 = os.path.join(REF, "third_party/ChamferDistancePytorch/chamfer6D")
+    jobs["chamfer6d"] = dict(
+        name="chamfer_6D",
+        sources=[os.path.join(c6, "chamfer_cuda.cpp"), os.path.join(c6, "chamfer6D.cu")],
+    )
     em = os.path.join(REF, "third_party/PyTorchEMD/cuda")
     jobs["emd"] = dict(
         name="emd_ext",
@@ -81,7 +87,7 @@ def build(which=None):
 def load_ref(key):
     """Import a prebuilt reference extension by file path (tests only). Returns module or None."""
     import importlib.util
-    names = {"pvcnn": "_pvcnn_backend", "chamfer": "chamfer_3D", "emd": "emd_ext"}
+    names = {"pvcnn": "_pvcnn_backend", "chamfer": "chamfer_3D", "emd": "emd_ext", "chamfer6d": "chamfer_6D"}
     so = os.path.join(OUT, key, names[key] + ".so")
     if not os.path.exists(so):
         return None

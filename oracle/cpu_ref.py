@@ -176,6 +176,30 @@ def chamfer_backward(xyz1, xyz2, gd1, gd2, idx1, idx2):
     return g1, g2
 
 
+def chamfer_nd_forward(xyz1, xyz2):
+    """chamfer{2,5,6}D forward (chamfer6D.cu:11-183); the dimension is the last axis of the inputs."""
+    xyz1, xyz2 = _f(xyz1), _f(xyz2)
+    b, n, dim = xyz1.shape
+    m = xyz2.shape[1]
+    d1 = np.zeros((b, n), np.float32)
+    d2 = np.zeros((b, m), np.float32)
+    i1 = np.zeros((b, n), np.int32)
+    i2 = np.zeros((b, m), np.int32)
+    lib().oracle_chamfer_nd_forward(_p(xyz1), _p(xyz2), b, n, m, dim, _p(d1), _p(d2), _p(i1), _p(i2))
+    return d1, d2, i1, i2
+
+
+def chamfer_nd_backward(xyz1, xyz2, gd1, gd2, idx1, idx2):
+    xyz1, xyz2, gd1, gd2, idx1, idx2 = _f(xyz1), _f(xyz2), _f(gd1), _f(gd2), _i(idx1), _i(idx2)
+    b, n, dim = xyz1.shape
+    m = xyz2.shape[1]
+    g1 = np.zeros((b, n, dim), np.float32)
+    g2 = np.zeros((b, m, dim), np.float32)
+    lib().oracle_chamfer_nd_backward(_p(xyz1), _p(xyz2), _p(gd1), _p(gd2), _p(idx1), _p(idx2), b, n, m, dim,
+                                     _p(g1), _p(g2))
+    return g1, g2
+
+
 def emd_approxmatch(xyz1, xyz2):
     xyz1, xyz2 = _f(xyz1), _f(xyz2)
     b, n, _ = xyz1.shape

@@ -331,6 +331,64 @@ API void oracle_chamfer_backward(const float* xyz1, const float* xyz2, const flo
   nm_grad(b, m, xyz2, n, xyz1, gd2, idx2, g2, g1);
 }
 
+/* ---- chamfer for D-dimensional points: chamfer6D.cu:11-183 (chunks of 2048; 2D: 512, 5D: 2048), :185-216 ------
+ * d = x*x + y*y + z*z + ... is contracted by nvcc into FMUL(y,y); FFMA(x,x,.); FFMA(z,z,.); ... (SASS of the compiled
+ * reference).  The reference's unrolled loop bound `end_k-(end_k&6)` (chamfer6D.cu:28) runs past the end of a
+ * chunk whose length is 1 or 3 mod 8 (it can return index m); this restatement (like the CUDA kernel) takes the true
+ * minimum. */
+static void nm_distance_nd(int dim, int b, int n, const float* xyz, int m, const float* xyz2, float* result,
+                           int* result_i) {
+  const int batch = dim == 2 ? 512 : 2048;
+#pragma omp parallel for collapse(2)
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < n; ++j) {
+      const float* a = xyz + ((size_t)i * n + j) * dim;
+      for (int k2 = 0; k2 < m; k2 += batch) {
+        const int end_k = imin(m, k2 + batch) - k2;
+        const float* buf = xyz2 + ((size_t)i * m + k2) * dim;
+        int best_i = 0;
+        float best = 0;
+        for (int k = 0; k < end_k; ++k) {
+          const float* o = buf + (size_t)k * dim;
+          float d = (o[1] - a[1]) * (o[1] - a[1]);
+          d = fmaf(o[0] - a[0], o[0] - a[0], d);
+          for (int c = 2; c < dim; ++c) d = fmaf(o[c] - a[c], o[c] - a[c], d);
+          if (k == 0 || d < best) { best = d; best_i = k + k2; }
+        }
+        if (k2 == 0 || result[(size_t)i * n + j] > best) {
+          result[(size_t)i * n + j] = best;
+          result_i[(size_t)i * n + j] = best_i;
+        }
+      }
+    }
+}
+API void oracle_chamfer_nd_forward(const float* xyz1, const float* xyz2, int b, int n, int m, int dim, float* dist1,
+                                   float* dist2, int* idx1, int* idx2) {
+  nm_distance_nd(dim, b, n, xyz1, m, xyz2, dist1, idx1);
+  nm_distance_nd(dim, b, m, xyz2, n, xyz1, dist2, idx2);
+}
+static void nm_grad_nd(int dim, int b, int n, const float* xyz1, int m, const float* xyz2, const float* gd,
+                       const int* idx, float* g1, float* g2) {
+  for (int i = 0; i < b; ++i)
+    for (int j = 0; j < n; ++j) {
+      const size_t a = ((size_t)i * n + j) * dim;
+      const int j2 = idx[(size_t)i * n + j];
+      const size_t c2 = ((size_t)i * m + j2) * dim;
+      const float g = gd[(size_t)i * n + j] * 2;
+      for (int d = 0; d < dim; ++d) {
+        const float t = g * (xyz1[a + d] - xyz2[c2 + d]);
+        g1[a + d] += t;
+        g2[c2 + d] += -t;
+      }
+    }
+}
+API void oracle_chamfer_nd_backward(const float* xyz1, const float* xyz2, const float* gd1, const float* gd2,
+                                    const int* idx1, const int* idx2, int b, int n, int m, int dim, float* g1,
+                                    float* g2) {
+  nm_grad_nd(dim, b, n, xyz1, m, xyz2, gd1, idx1, g1, g2);
+  nm_grad_nd(dim, b, m, xyz2, n, xyz1, gd2, idx2, g2, g1);
+}
+
 /* ---- EMD: emd_kernel.cu:24-156 (approxmatch), :199-241 (matchcost), :285-353 (gradients) -------------- */
 /* --use_fast_math (PyTorchEMD/backend.py:20): __expf(x) = ex2.approx.ftz(x * log2(e)) with the product rounded to
  * fp32 first.  That rounding is the dominant deviation from libm expf for large |x|, so it is restated; the

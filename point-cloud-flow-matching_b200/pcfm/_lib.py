@@ -54,6 +54,8 @@ SIGNATURES = {
     "pcfm_emd_matchcost_workspace": (_sz, [_i, _i, _i]),
     "pcfm_emd_matchcost_forward": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_emd_matchcost_backward": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "pcfm_chamfer_nd_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "pcfm_chamfer_nd_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "pcfm_chamfer3d_allpairs": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "pcfm_emd_allpairs_workspace": (_sz, [_i, _i, _i, _i]),
     "pcfm_emd_allpairs": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),

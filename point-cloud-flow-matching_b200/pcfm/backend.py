@@ -319,6 +319,39 @@ class _Chamfer3D:
         return 1
 
 
+class _ChamferND:
+    """`chamfer_2D` / `chamfer_5D` / `chamfer_6D` (chamfer6D/chamfer_cuda.cpp:30-33): same contract as `chamfer_3D` for
+    points with `dim` coordinates."""
+
+    def __init__(self, dim):
+        self.dim = dim
+
+    def forward(self, xyz1, xyz2, dist1, dist2, idx1, idx2):
+        b, n, d = xyz1.shape
+        m = xyz2.shape[1]
+        if d != self.dim or xyz2.shape[2] != self.dim:
+            raise RuntimeError(f"chamfer_{self.dim}D: last dimension must be {self.dim}")
+        with torch.cuda.device(xyz1.device):
+            rc = lib.pcfm_chamfer_nd_forward(_ptr(xyz1), _ptr(xyz2), b, n, m, d, _ptr(dist1), _ptr(dist2),
+                                             _ptr(idx1), _ptr(idx2), _stream(xyz1))
+        if rc != 0:
+            print(f"error in nnd updateOutput: pcfm rc={rc}")
+            return 0
+        return 1
+
+    def backward(self, xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2):
+        b, n, d = xyz1.shape
+        m = xyz2.shape[1]
+        with torch.cuda.device(xyz1.device):
+            rc = lib.pcfm_chamfer_nd_backward(_ptr(xyz1), _ptr(xyz2), _ptr(graddist1), _ptr(graddist2), _ptr(idx1),
+                                              _ptr(idx2), b, n, m, d, _ptr(gradxyz1), _ptr(gradxyz2),
+                                              _stream(xyz1))
+        if rc != 0:
+            print(f"error in nnd get grad: pcfm rc={rc}")
+            return 0
+        return 1
+
+
 class _EmdExt:
     """`emd_ext` / `emd_cuda_dynamic` (emd.cpp:23-27)."""
 
@@ -372,6 +405,7 @@ class _EmdExt:
 
 pvcnn = _PvcnnBackend()
 chamfer = _Chamfer3D()
+chamfer_2d, chamfer_5d, chamfer_6d = _ChamferND(2), _ChamferND(5), _ChamferND(6)
 emd = _EmdExt()
 
 

@@ -1,6 +1,7 @@
 """Chamfer-3D and approximate-EMD operators with the reference's Python signatures.
 
   chamfer_3DFunction / chamfer_3DDist / *_noGrad   <- ChamferDistancePytorch/chamfer3D/dist_chamfer_3D.py:41-133
+  chamfer_{2,5,6}DFunction / chamfer_{2,5,6}DDist   <- ChamferDistancePytorch/chamfer6D/dist_chamfer_6D.py:30-82 (and 2D, 5D)
   EarthMoverDistanceFunction / earth_mover_distance <- PyTorchEMD/emd.py:6-51
   earth_mover_distance_nograd                       <- PyTorchEMD/emd_nograd.py:7-44
 Inputs are cast to float32 under autocast exactly like the reference's custom_fwd(cast_inputs=float32).
@@ -11,6 +12,7 @@ from torch.amp import custom_bwd, custom_fwd
 from torch.autograd import Function
 
 from .backend import chamfer as chamfer_3D
+from .backend import chamfer_2d, chamfer_5d, chamfer_6d
 from .backend import emd as emd_cuda
 
 
@@ -55,6 +57,47 @@ class chamfer_3DFunction(Function):
 class chamfer_3DDist(nn.Module):
     def forward(self, input1, input2):
         return chamfer_3DFunction.apply(input1.contiguous(), input2.contiguous())
+
+
+def _make_chamfer_nd(dim, ext):
+    """chamfer_<dim>DFunction / chamfer_<dim>DDist with the reference's contract (dist_chamfer_6D.py:30-82)."""
+
+    class _Fn(Function):
+        @staticmethod
+        def forward(ctx, xyz1, xyz2):
+            b, n, d = xyz1.size()
+            assert d == dim, "Wrong last dimension for the chamfer distance 's input! Check with .size()"
+            _, m, d2 = xyz2.size()
+            assert d2 == dim, "Wrong last dimension for the chamfer distance 's input! Check with .size()"
+            dev = xyz1.device
+            dist1 = torch.zeros(b, n, device=dev)
+            dist2 = torch.zeros(b, m, device=dev)
+            idx1 = torch.zeros(b, n, dtype=torch.int32, device=dev)
+            idx2 = torch.zeros(b, m, dtype=torch.int32, device=dev)
+            ext.forward(xyz1, xyz2, dist1, dist2, idx1, idx2)
+            ctx.save_for_backward(xyz1, xyz2, idx1, idx2)
+            return dist1, dist2, idx1, idx2
+
+        @staticmethod
+        def backward(ctx, graddist1, graddist2, gradidx1, gradidx2):
+            xyz1, xyz2, idx1, idx2 = ctx.saved_tensors
+            g1 = torch.zeros_like(xyz1)
+            g2 = torch.zeros_like(xyz2)
+            ext.backward(xyz1, xyz2, g1, g2, graddist1.contiguous(), graddist2.contiguous(), idx1, idx2)
+            return g1, g2
+
+    class _Dist(nn.Module):
+        def forward(self, input1, input2):
+            return _Fn.apply(input1.contiguous().float(), input2.contiguous().float())
+
+    _Fn.__name__ = _Fn.__qualname__ = f"chamfer_{dim}DFunction"
+    _Dist.__name__ = _Dist.__qualname__ = f"chamfer_{dim}DDist"
+    return _Fn, _Dist
+
+
+chamfer_2DFunction, chamfer_2DDist = _make_chamfer_nd(2, chamfer_2d)
+chamfer_5DFunction, chamfer_5DDist = _make_chamfer_nd(5, chamfer_5d)
+chamfer_6DFunction, chamfer_6DDist = _make_chamfer_nd(6, chamfer_6d)
 
 
 class chamfer_3DFunction_noGrad(Function):

@@ -29,17 +29,17 @@ def devox_case(seed, b, c, n, res):
     return np.clip(coords, 0, res - 1).astype(np.float32), vox, gy, res
 
 
-def cloud_pair(seed, b, n, m, kind="randn"):
+def cloud_pair(seed, b, n, m, kind="randn", dim=3):
     r = _r(seed)
     if kind == "lattice":  # exact ties and duplicated points
-        a = (r.integers(0, 6, size=(b, n, 3)) * 0.125).astype(np.float32)
-        c = (r.integers(0, 6, size=(b, m, 3)) * 0.125).astype(np.float32)
+        a = (r.integers(0, 6, size=(b, n, dim)) * 0.125).astype(np.float32)
+        c = (r.integers(0, 6, size=(b, m, dim)) * 0.125).astype(np.float32)
     elif kind == "rand":
-        a = r.random((b, n, 3)).astype(np.float32)
-        c = r.random((b, m, 3)).astype(np.float32)
+        a = r.random((b, n, dim)).astype(np.float32)
+        c = r.random((b, m, dim)).astype(np.float32)
     else:
-        a = r.standard_normal((b, n, 3)).astype(np.float32)
-        c = r.standard_normal((b, m, 3)).astype(np.float32)
+        a = r.standard_normal((b, n, dim)).astype(np.float32)
+        c = r.standard_normal((b, m, dim)).astype(np.float32)
     return a, c
 
 
@@ -63,6 +63,14 @@ VOXEL = {
 DEVOX = {
     "devox_r16": dict(seed=11, b=2, c=6, n=1500, res=16),
     "devox_r5": dict(seed=12, b=1, c=3, n=333, res=5),
+}
+# 6-D clouds (xyz + rgb).  Chunk lengths (cloud size mod 2048) avoid 1 and 3 (mod 8): there the reference's unrolled
+# loop bound (chamfer6D.cu:28 `end_k-(end_k&6)`, `&3` in chamfer3D.cu) runs two / one points past the end of the chunk
+# and can return an out-of-range index (observed on a B200: idx 513 for m = 513)
+CHAMFER6D = {
+    "ch6_unit": dict(seed=24, b=3, n=100, m=200, kind="rand", dim=6),
+    "ch6_lattice": dict(seed=25, b=2, n=700, m=516, kind="lattice", dim=6),
+    "ch6_big": dict(seed=26, b=1, n=2500, m=2300, kind="randn", dim=6),   # two chunks of the 2048-point tile
 }
 CHAMFER = {
     "ch_unit": dict(seed=21, b=4, n=100, m=200, kind="rand"),       # unit_test.py:15-16 shapes

@@ -1,7 +1,8 @@
 """Generate golden vectors by running the UNMODIFIED reference CUDA extensions (oracle/_ref, built by
 oracle/build_ref.py from /root/reference) on a GPU.  Run on the B200 box:
 
-    python tests/golden/make_golden.py        # writes tests/golden/ref_b200.npz (and gpurun_out/ref_b200.npz)
+    python tests/golden/make_golden.py            # writes tests/golden/ref_b200.npz (and gpurun_out/ref_b200.npz)
+    python tests/golden/make_golden.py chamfer6d  # writes tests/golden/ref_b200_chamfer6d.npz
 
 Only integer outputs (bit-exact) and small float outputs are stored; inputs are regenerated from seeds (cases.py).
 """
@@ -27,7 +28,32 @@ def n(x):
     return x.detach().cpu().numpy()
 
 
+def chamfer6d():
+    """tests/golden/ref_b200_chamfer6d.npz: the compiled reference chamfer_6D on the 6-D cases."""
+    c6 = build_ref.load_ref("chamfer6d")
+    assert c6, "oracle/_ref/chamfer6d is not built"
+    out = {}
+    for name, kw in cases.CHAMFER6D.items():
+        a, c = cases.cloud_pair(**kw)
+        b, nn_, m = a.shape[0], a.shape[1], c.shape[1]
+        d1 = torch.zeros(b, nn_).cuda(); d2 = torch.zeros(b, m).cuda()
+        i1 = torch.zeros(b, nn_, dtype=torch.int32).cuda(); i2 = torch.zeros(b, m, dtype=torch.int32).cuda()
+        assert c6.forward(t(a), t(c), d1, d2, i1, i2) == 1
+        g1 = torch.zeros(b, nn_, 6).cuda(); g2 = torch.zeros(b, m, 6).cuda()
+        gd1 = torch.ones(b, nn_).cuda(); gd2 = (torch.arange(m).float() / m).repeat(b, 1).cuda()
+        c6.backward(t(a), t(c), g1, g2, gd1, gd2, i1, i2)
+        out[name + "/dist1"] = n(d1); out[name + "/dist2"] = n(d2)
+        out[name + "/idx1"] = n(i1); out[name + "/idx2"] = n(i2)
+        out[name + "/g1"] = n(g1); out[name + "/g2"] = n(g2)
+    for dst in (os.path.join(HERE, "ref_b200_chamfer6d.npz"), os.path.join(ROOT, "gpurun_out", "ref_b200_chamfer6d.npz")):
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        np.savez_compressed(dst, **out)
+        print("wrote", dst, os.path.getsize(dst) // 1024, "KiB")
+
+
 def main():
+    if "chamfer6d" in sys.argv[1:]:
+        return chamfer6d()
     pv = build_ref.load_ref("pvcnn")
     ch = build_ref.load_ref("chamfer")
     em = build_ref.load_ref("emd")

@@ -44,7 +44,7 @@ def ref():
     """The compiled reference extensions (None if oracle/_ref is absent)."""
     from oracle import build_ref
     out = {}
-    for k in ("pvcnn", "chamfer", "emd"):
+    for k in ("pvcnn", "chamfer", "emd", "chamfer6d"):
         try:
             out[k] = build_ref.load_ref(k)
         except Exception as e:  # noqa: BLE001
@@ -350,6 +350,58 @@ def test_chamfer_autograd_wrapper(be, oracle):
     od1, od2, oi1, oi2 = oracle.chamfer_forward(a, c)
     og1, og2 = oracle.chamfer_backward(a, c, np.ones_like(od1), 0.5 * np.ones_like(od2), oi1, oi2)
     assert_close(host(x1.grad), og1, "grad1"); assert_close(host(x2.grad), og2, "grad2")
+
+
+# ------------------------------------------------------------------------------------------------ chamfer 2D / 5D / 6D
+CHND_SHAPES = [dict(dim=6, **{k: v for k, v in kw.items() if k != "dim"}) for kw in cases.CHAMFER6D.values()] + [
+    dict(seed=28, b=2, n=300, m=900, kind="lattice", dim=2),
+    dict(seed=29, b=2, n=1200, m=333, kind="randn", dim=5),
+    dict(seed=30, b=8, n=20000, m=2048, kind="rand", dim=6),     # two own points per thread
+    dict(seed=30, b=1, n=1, m=1, kind="rand", dim=6),
+]
+
+
+@pytest.mark.parametrize("kw", CHND_SHAPES, ids=lambda k: f"d{k['dim']}{k['kind']}b{k['b']}n{k['n']}m{k['m']}")
+def test_chamfer_nd(be, oracle, ref, kw):
+    """chamfer_2D / 5D / 6D (ChamferDistancePytorch/chamfer6D/chamfer6D.cu): bit-exact distances and arg-mins vs the
+    oracle and, for D = 6, vs the compiled reference extension."""
+    a, c = cases.cloud_pair(**kw)
+    dim = kw["dim"]
+    mod = {2: be.chamfer_2d, 5: be.chamfer_5d, 6: be.chamfer_6d}[dim]
+    d1, d2, i1, i2 = run_chamfer(mod, a, c)
+    od1, od2, oi1, oi2 = oracle.chamfer_nd_forward(a, c)
+    assert_equal(host(i1), oi1, "idx1"); assert_equal(host(i2), oi2, "idx2")
+    assert_equal(host(d1), od1, "dist1"); assert_equal(host(d2), od2, "dist2")
+    b, n, m = a.shape[0], a.shape[1], c.shape[1]
+    gd1 = rng(kw["seed"] + 1).standard_normal((b, n)).astype(np.float32)
+    gd2 = rng(kw["seed"] + 2).standard_normal((b, m)).astype(np.float32)
+    g1 = torch.zeros(b, n, dim, device="cuda"); g2 = torch.zeros(b, m, dim, device="cuda")
+    assert mod.backward(cu(a), cu(c), g1, g2, cu(gd1), cu(gd2), i1, i2) == 1
+    og1, og2 = oracle.chamfer_nd_backward(a, c, gd1, gd2, oi1, oi2)
+    assert_close(host(g1), og1, "gradxyz1"); assert_close(host(g2), og2, "gradxyz2")
+    if dim == 6 and ref.get("chamfer6d") is not None and m % 8 not in (1, 3) and n % 8 not in (1, 3):
+        rd1, rd2, ri1, ri2 = run_chamfer(ref["chamfer6d"], a, c)
+        assert_equal(host(i1), host(ri1), "idx1 vs reference"); assert_equal(host(i2), host(ri2), "idx2 vs reference")
+        assert_equal(host(d1), host(rd1), "dist1 vs reference"); assert_equal(host(d2), host(rd2), "dist2 vs reference")
+
+
+def test_chamfer_6d_autograd_wrapper_and_3d_consistency(be, oracle):
+    """dist_chamfer_6D.py:30-82 contract; with the last three coordinates equal in both clouds the 6-D distance is the
+    3-D one."""
+    from pcfm.metrics import chamfer_3DDist, chamfer_6DDist
+    a, c = cases.cloud_pair(seed=27, b=2, n=300, m=200, dim=6)
+    x1 = cu(a).requires_grad_(True); x2 = cu(c).requires_grad_(True)
+    d1, d2, i1, i2 = chamfer_6DDist()(x1, x2)
+    (d1.sum() + 0.5 * d2.sum()).backward()
+    od1, od2, oi1, oi2 = oracle.chamfer_nd_forward(a, c)
+    og1, og2 = oracle.chamfer_nd_backward(a, c, np.ones_like(od1), 0.5 * np.ones_like(od2), oi1, oi2)
+    assert_close(host(x1.grad), og1, "grad1"); assert_close(host(x2.grad), og2, "grad2")
+    a[..., 3:] = 0.25; c[..., 3:] = 0.25
+    e1, e2, j1, j2 = chamfer_6DDist()(cu(a), cu(c))
+    f1, f2, k1, k2 = chamfer_3DDist()(cu(a[..., :3].copy()), cu(c[..., :3].copy()))
+    assert torch.equal(e1, f1) and torch.equal(e2, f2) and torch.equal(j1, k1) and torch.equal(j2, k2)
+    with pytest.raises(AssertionError):
+        chamfer_6DDist()(cu(a[..., :3].copy()), cu(c[..., :3].copy()))
 
 
 # ------------------------------------------------------------------------------------------------ EMD

@@ -68,6 +68,40 @@ def test_golden_chamfer(golden, name):
     assert_close(g1, golden[name + "/g1"], "g1"); assert_close(g2, golden[name + "/g2"], "g2")
 
 
+GOLDEN6 = os.path.join(HERE, "golden", "ref_b200_chamfer6d.npz")
+
+
+@pytest.mark.parametrize("name", sorted(cases.CHAMFER6D))
+def test_golden_chamfer_6d(name):
+    """The compiled reference chamfer_6D (oracle/_ref/chamfer6d) run on a B200: bit-exact distances and indices."""
+    if not os.path.exists(GOLDEN6):
+        pytest.skip("tests/golden/ref_b200_chamfer6d.npz not generated (python tests/golden/make_golden.py chamfer6d)")
+    golden = np.load(GOLDEN6)
+    a, c = cases.cloud_pair(**cases.CHAMFER6D[name])
+    d1, d2, i1, i2 = o.chamfer_nd_forward(a, c)
+    assert_equal(i1, golden[name + "/idx1"], "idx1"); assert_equal(i2, golden[name + "/idx2"], "idx2")
+    assert_equal(d1, golden[name + "/dist1"], "dist1"); assert_equal(d2, golden[name + "/dist2"], "dist2")
+    m = c.shape[1]
+    gd1 = np.ones_like(d1); gd2 = np.tile(np.arange(m, dtype=np.float32) / m, (a.shape[0], 1))
+    g1, g2 = o.chamfer_nd_backward(a, c, gd1, gd2, i1, i2)
+    assert_close(g1, golden[name + "/g1"], "g1"); assert_close(g2, golden[name + "/g2"], "g2")
+
+
+def test_chamfer_nd_reduces_to_3d_and_matches_float64():
+    """With the extra coordinates equal in both clouds the 6-D operator is the 3-D one bit for bit; on random 5-D /
+    2-D clouds it matches the float64 pairwise method (unit_test.py:14-35 criterion)."""
+    a, c = cases.cloud_pair(seed=71, b=2, n=400, m=300, kind="lattice")
+    a6 = np.concatenate([a, np.full_like(a, 0.5)], 2); c6 = np.concatenate([c, np.full_like(c, 0.5)], 2)
+    for x, y in zip(o.chamfer_nd_forward(a6, c6), o.chamfer_forward(a, c)):
+        assert_equal(x, y, "6D with constant tail vs 3D")
+    for dim in (2, 5):
+        p, q = cases.cloud_pair(seed=72 + dim, b=3, n=150, m=260, kind="rand", dim=dim)
+        d1, d2, i1, i2 = o.chamfer_nd_forward(p, q)
+        D = ((p[:, :, None, :].astype(np.float64) - q[:, None, :, :]) ** 2).sum(-1)
+        assert float(((d1 - D.min(2)) ** 2).mean() + ((d2 - D.min(1)) ** 2).mean()) < 1e-8
+        assert_equal(i1, D.argmin(2).astype(np.int32), "idx1"); assert_equal(i2, D.argmin(1).astype(np.int32), "idx2")
+
+
 @pytest.mark.parametrize("name", sorted(cases.EMD))
 def test_golden_emd(golden, name):
     a, c = cases.cloud_pair(**cases.EMD[name])
