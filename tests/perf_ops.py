@@ -45,7 +45,7 @@ def main():
     ref = None
     if args.ref:
         from oracle import build_ref
-        ref = {k: build_ref.load_ref(k) for k in ("pvcnn", "chamfer", "emd")}
+        ref = {k: build_ref.load_ref(k) for k in ("pvcnn", "chamfer", "emd", "chamfer6d")}
     dev = "cuda"
     _lib.set_option("plan", args.plan)
     for kv in filter(None, args.opt.split(",")):
@@ -170,6 +170,17 @@ def main():
             row["Gevals_per_s"] = round(2 * b * n * m / row["ms"] / 1e6, 1)
             if ref and ref["chamfer"] is not None:
                 row["ms_reference_cuda"] = round(timeit(lambda: ref["chamfer"].forward(a, c2, d1, d2, i1, i2), iters=3, warm=1), 3)
+            rows.append(row); print(json.dumps(row), flush=True)
+    if not only or "chamfer" in only:
+        for (b, n, m) in [(32, 2000, 1000), (2, 2048, 2048), (8, 20000, 20000)]:
+            a = torch.rand(b, n, 6, device=dev, generator=g); c2 = torch.rand(b, m, 6, device=dev, generator=g)
+            d1 = torch.zeros(b, n, device=dev); d2 = torch.zeros(b, m, device=dev)
+            i1 = torch.zeros(b, n, dtype=torch.int32, device=dev); i2 = torch.zeros(b, m, dtype=torch.int32, device=dev)
+            row = {"op": "chamfer6d_fwd", "B": b, "N": n, "M": m,
+                   "ms": round(timeit(lambda: be.chamfer_6d.forward(a, c2, d1, d2, i1, i2)), 4)}
+            row["Gevals_per_s"] = round(2 * b * n * m / row["ms"] / 1e6, 1)
+            if ref and ref.get("chamfer6d") is not None:
+                row["ms_reference_cuda"] = round(timeit(lambda: ref["chamfer6d"].forward(a, c2, d1, d2, i1, i2), iters=3, warm=1), 3)
             rows.append(row); print(json.dumps(row), flush=True)
     if not only or "emd" in only:
         for (b, n) in [(8, 1024), (32, 2048)]:
