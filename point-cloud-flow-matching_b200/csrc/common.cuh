@@ -21,6 +21,7 @@ extern int g_opt_stage;
 extern int g_opt_devox_il;      // 1 = channel-interleaved planes in devoxelize forward when G >= 4 (default)
 extern int g_opt_pdl;           // 1 = row kernels overlap the tail of the fused plan kernel (PDL), 0 = plain launches
 extern int g_opt_fps;           // 0 = cluster FPS (points in registers) when the cloud fits, 1 = one CTA per cloud
+extern int g_opt_gather_bwd;    // 0 = gather backward with atomics (like the reference), 1 = sorted-segment sums
 extern int g_opt_plan;          // 0 = fused cell-plan build when it fits, 1 = always the multi-kernel build
 extern int g_num_sms;           // cached SM count of the current device (148 on B200)
 int num_sms();

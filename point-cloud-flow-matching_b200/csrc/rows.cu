@@ -377,6 +377,17 @@ static size_t scatter_ws(int b, long long e, long long t) {
   return csr_workspace_bytes(b, e, t, false) + align256((size_t)b * t * sizeof(int)) + 256;
 }
 
+__global__ void __launch_bounds__(256) gather_bwd_atomic_kernel(const float* __restrict__ grad_y,
+                                                                const int* __restrict__ indices, int c, int n, int m,
+                                                                float* __restrict__ grad_x) {
+  const int b = blockIdx.z, ch = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= m) return;
+  const int t = indices[(long long)b * m + j];
+  if (t < 0 || t >= n) return;
+  atomicAdd(grad_x + ((long long)b * c + ch) * n + t, grad_y[((long long)b * c + ch) * m + j]);
+}
+
 static int scatter_unit(const float* grad_y, const int* indices, int b, int c, int t, int e, float* grad_x,
                         void* workspace, size_t workspace_bytes, cudaStream_t st) {
   Workspace ws(workspace, workspace_bytes);
@@ -423,6 +434,18 @@ int pcfm_gather_features_backward(const float* grad_y, const int* indices, int b
   if (b < 0 || c < 0 || n < 0 || m < 0) return PCFM_E_BADARG;
   if (b == 0 || c == 0 || n == 0) return 0;
   if (!grad_x || (m > 0 && (!grad_y || !indices))) return PCFM_E_BADARG;
+  if (g_opt_gather_bwd == 0) {
+    // sampling.cu:62-84: zero + one atomicAdd per (channel, sample).  Sampled indices are normally distinct (FPS), so
+    // a target receives one addend and the result does not depend on the order; a plan build (the sorted-segment path
+    // below) costs 3-5x the whole operator at these sizes (B*C*M ~ 10^6).
+    cudaStream_t st = (cudaStream_t)stream;
+    PCFM_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)b * c * n * sizeof(float), st));
+    if (m == 0) return 0;
+    dim3 grid(cdiv(m, 256), c, b);
+    gather_bwd_atomic_kernel<<<grid, 256, 0, st>>>(grad_y, indices, c, n, m, grad_x);
+    PCFM_LAUNCHED();
+    return 0;
+  }
   return scatter_unit(grad_y, indices, b, c, n, m, grad_x, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 

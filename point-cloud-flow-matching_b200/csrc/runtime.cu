@@ -9,6 +9,7 @@ int g_opt_devox_bwd = 0;
 int g_opt_vox_fwd = 0;
 int g_opt_stage = 0;
 int g_opt_plan = 0;
+int g_opt_gather_bwd = 0;
 int g_opt_fps = 0;
 int g_opt_pdl = 1;
 int g_opt_devox_il = 1;
@@ -46,6 +47,7 @@ int pcfm_set_option(const char* key, int value) {
   if (!strcmp(key, "devox_il")) { pcfm::g_opt_devox_il = value; return 0; }
   if (!strcmp(key, "pdl")) { pcfm::g_opt_pdl = value; return 0; }
   if (!strcmp(key, "fps")) { pcfm::g_opt_fps = value; return 0; }
+  if (!strcmp(key, "gather_bwd")) { pcfm::g_opt_gather_bwd = value; return 0; }
   if (!strcmp(key, "plan")) { pcfm::g_opt_plan = value; return 0; }
   return PCFM_E_BADARG;
 }

@@ -255,7 +255,18 @@ def test_fps_ballquery_grouping_gather_3nn(be, oracle, ref, kw):
     ggx = be.pvcnn.grouping_backward(cu(ggy), bq, n)
     assert_close(host(ggx), oracle.grouping_backward(ggy, host(bq), n), "grouping backward")
     gg = be.pvcnn.gather_features_backward(cu(cfeat), fidx, n)
-    assert_close(host(gg), oracle.gather_backward(cfeat, o_fidx, n), "gather backward")
+    distinct = all(len(np.unique(row)) == m for row in o_fidx)   # FPS repeats index 0 once a lattice cloud is used up
+    check = assert_equal if distinct else assert_close
+    check(host(gg), oracle.gather_backward(cfeat, o_fidx, n), "gather backward (distinct indices: exact)")
+    from pcfm import _lib
+    _lib.set_option("gather_bwd", 1)          # sorted-segment variant
+    try:
+        check(host(be.pvcnn.gather_features_backward(cu(cfeat), fidx, n)), host(gg), "gather backward variants")
+    finally:
+        _lib.set_option("gather_bwd", 0)
+    dup = fidx.clone(); dup[:, 1::2] = dup[:, ::2][:, :dup[:, 1::2].shape[1]]   # duplicated samples accumulate
+    assert_close(host(be.pvcnn.gather_features_backward(cu(cfeat), dup, n)),
+                 oracle.gather_backward(cfeat, host(dup), n), "gather backward with repeated indices")
     o3, i3, w3 = be.pvcnn.three_nearest_neighbors_interpolate_forward(cu(pts), centers, cu(cfeat))
     oo3, oi3, ow3 = oracle.three_nn_interpolate_forward(pts, o_centers, cfeat)
     assert_equal(host(i3), oi3, "3nn indices")
