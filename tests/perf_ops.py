@@ -106,7 +106,7 @@ def main():
                 _lib.set_option("devox_bwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4); _lib.set_option("devox_bwd", 0)
             if op in ("vox_fwd", "devox_fwd"):
                 _lib.set_option("stage", 1); row["ms_plain_stage"] = round(timeit(fn), 4); _lib.set_option("stage", 0)
-            if ref and ref["pvcnn"] is not None:
+            if ref and ref["pvcnn"] is not None and op != "plan_mean":
                 R = ref["pvcnn"]
                 rf = {"vox_fwd": lambda: R.avg_voxelize_forward(feat, vox, r),
                       "vox_bwd": lambda: R.avg_voxelize_backward(grid, ind, cnt),
