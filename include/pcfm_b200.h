@@ -99,9 +99,10 @@ int pcfm_trilinear_devoxelize_backward(const float* grad_y, const int* inds, con
 
 /* Same result as pcfm_trilinear_devoxelize_backward for the inds/wgts that pcfm_trilinear_devoxelize_forward derives
  * from `coords` (f32[B,3,N] in [0,r-1]), but takes the coordinates themselves: the 8 weights are recomputed with the
- * forward's exact arithmetic and every point is visited once per channel (cell-sorted plan, no atomics).  This is the
- * entry the autograd wrapper uses (it saves `coords` next to the reference's inds/wgts).  Requires r^3 floats to fit
- * in shared memory (r <= 37); returns PCFM_E_BADARG otherwise (use the generic entry above). */
+ * forward's exact arithmetic and every point is visited once per channel (cell-sorted plan).  This is the entry the
+ * autograd wrapper uses (it saves `coords` next to the reference's inds/wgts).  r <= 37: the channel plane accumulates
+ * in shared memory (no global atomics, no memset); 38 <= r <= 256: grad_x is zeroed and the per-cell corner sums are
+ * added with global atomics (8 per cell instead of the reference's 8 per point). */
 size_t pcfm_trilinear_devoxelize_backward_coords_workspace(int b, int c, int n, int r);
 int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* coords, int b, int c, int n, int r,
                                               float* grad_x, void* workspace, size_t workspace_bytes,

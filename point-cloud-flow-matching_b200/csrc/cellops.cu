@@ -133,7 +133,9 @@ __device__ __forceinline__ void tri_accumulate(float fx, float fy, float fz, flo
   s[7] = fmaf(a11, gz1, s[7]);
 }
 
-template <bool ROW_SMEM>
+// PLANE_SMEM = false (grids whose plane does not fit in shared memory, r >= 38): the cell sums are added straight into
+// the caller-zeroed output with global atomics (RED.ADD.F32) — 8 per CELL, where the reference issues 8 per point.
+template <bool ROW_SMEM, bool PLANE_SMEM>
 __global__ void __launch_bounds__(1024, 1)
     devox_bwd_cell_kernel(const float* __restrict__ grad_y, const int* __restrict__ cells,
                           const int* __restrict__ slot0, const int* __restrict__ meta,
@@ -144,11 +146,11 @@ __global__ void __launch_bounds__(1024, 1)
   __shared__ uint64_t bar;
   __shared__ int next_item;
   const int r2 = r * r, P = r2 * r;
-  float* plane = smem;                 // [P]
-  float* row = smem + ((P + 3) & ~3);  // [N] (ROW_SMEM)
   const int c = blockIdx.x, b = blockIdx.y;
   const float* row_g = grad_y + ((long long)b * C + c) * N;
   float* o = grad_x + ((long long)b * C + c) * P;
+  float* plane = PLANE_SMEM ? smem : o;                   // [P]
+  float* row = smem + (PLANE_SMEM ? ((P + 3) & ~3) : 0);  // [N] (ROW_SMEM)
   if (threadIdx.x == 0) {
     mbar_init(&bar, 1);
     fence_mbar_init();
@@ -162,7 +164,7 @@ __global__ void __launch_bounds__(1024, 1)
     for (uint32_t off = 0; off < (uint32_t)bulk * 4u; off += kBulkChunk)
       bulk_g2s((char*)row + off, (const char*)row_g + off, min(kBulkChunk, (uint32_t)bulk * 4u - off), &bar);
   }
-  for (int i = threadIdx.x; i < ((P + 3) >> 2); i += blockDim.x)  // overlaps the row copy
+  for (int i = threadIdx.x; PLANE_SMEM && i < ((P + 3) >> 2); i += blockDim.x)  // overlaps the row copy
     ((float4*)plane)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ROW_SMEM) {
     for (int i = bulk + threadIdx.x; i < N; i += blockDim.x) row[i] = __ldg(row_g + i);
@@ -279,6 +281,7 @@ __global__ void __launch_bounds__(1024, 1)
       }
     }
   }
+  if (!PLANE_SMEM) return;
   __syncthreads();
   // ---- write the plane: one bulk (TMA) store when aligned, else a coalesced copy ----
   if ((((uintptr_t)o) & 15) == 0 && (P & 3) == 0 && use_tma) {
@@ -295,8 +298,8 @@ __global__ void __launch_bounds__(1024, 1)
   }
 }
 
-static size_t devox_bwd_smem(int n, int r, bool row_smem) {
-  const size_t p = (size_t)r * r * r;
+static size_t devox_bwd_smem(int n, int r, bool row_smem, bool plane_smem = true) {
+  const size_t p = plane_smem ? (size_t)r * r * r : 0;
   return (((p + 3) & ~(size_t)3) + (row_smem ? n : 0)) * sizeof(float);
 }
 constexpr size_t kSmemLimit = 227 * 1024 - 512;  // opt-in maximum (232448 B) minus the static shared memory
@@ -369,11 +372,12 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
   if (!grad_x || (n > 0 && (!grad_y || !coords))) return PCFM_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
   const long long tl = (long long)r * r * r;
-  if (devox_bwd_smem(0, r, false) > kSmemLimit || tl > (1 << 24)) return PCFM_E_BADARG;  // plane must fit (r <= 37)
+  if (tl > (1 << 24)) return PCFM_E_BADARG;  // 24-bit cell ids in the plan (r <= 256)
   const int t = (int)tl;
-  if (n == 0) {
+  const bool plane_smem = devox_bwd_smem(0, r, false) <= kSmemLimit;  // r <= 37
+  if (n == 0 || !plane_smem) {
     PCFM_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)b * c * t * sizeof(float), st));
-    return 0;
+    if (n == 0) return 0;
   }
   Workspace ws(workspace, workspace_bytes);
   CellPlan plan;
@@ -381,26 +385,30 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
   if (rc) return rc;
   static bool attr_set = false;
   if (!attr_set) {
-    PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kSmemLimit));
-    PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   (int)kSmemLimit));
+    PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    (int)kSmemLimit));
     attr_set = true;
   }
   dim3 grid(c, b);
-  const bool row_smem = devox_bwd_smem(n, r, true) <= kSmemLimit;
-  // small planes (r <= 16): two CTAs of 512 threads per SM overlap one CTA's staging with the other's compute
-  const int threads = (row_smem && devox_bwd_smem(n, r, true) <= 110 * 1024) ? 512 : 1024;
-  if (row_smem)
-    PCFM_CUDA(launch_dependent(devox_bwd_cell_kernel<true>, grid, dim3(threads), devox_bwd_smem(n, r, true), st,
-                               plan.pdl, grad_y, plan.cells, plan.slot0, plan.meta, plan.heavy,
-                               (const float4*)plan.rec, grad_x, c, n, r, plan.lcap, plan.hcap, plan.rcap,
-                               (int)(g_opt_stage == 0)));
-  else
-    PCFM_CUDA(launch_dependent(devox_bwd_cell_kernel<false>, grid, dim3(threads), devox_bwd_smem(n, r, false), st,
-                               plan.pdl, grad_y, plan.cells, plan.slot0, plan.meta, plan.heavy,
-                               (const float4*)plan.rec, grad_x, c, n, r, plan.lcap, plan.hcap, plan.rcap,
-                               (int)(g_opt_stage == 0)));
+  const bool row_smem = devox_bwd_smem(n, r, true, plane_smem) <= kSmemLimit;
+  const size_t smem = devox_bwd_smem(n, r, row_smem, plane_smem);
+  // small footprints (r <= 16, or no plane): two CTAs of 512 threads per SM overlap one CTA's staging with the
+  // other's compute
+  const int threads = (row_smem && smem <= 110 * 1024) ? 512 : 1024;
+  const int tma = (int)(g_opt_stage == 0);
+#define PCFM_DBWD(RS, PS)                                                                                         \
+  PCFM_CUDA(launch_dependent(devox_bwd_cell_kernel<RS, PS>, grid, dim3(threads), smem, st, plan.pdl, grad_y,       \
+                             plan.cells, plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec, grad_x, c, n, \
+                             r, plan.lcap, plan.hcap, plan.rcap, tma))
+  if (plane_smem && row_smem) PCFM_DBWD(true, true);
+  else if (plane_smem) PCFM_DBWD(false, true);
+  else if (row_smem) PCFM_DBWD(true, false);
+  else PCFM_DBWD(false, false);
+#undef PCFM_DBWD
   PCFM_LAUNCHED();
   return 0;
 }

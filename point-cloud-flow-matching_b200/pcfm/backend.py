@@ -149,7 +149,7 @@ class _PvcnnBackend:
                   "trilinear_devoxelize_backward")
         return grad_x
 
-    MAX_FAST_DEVOX_BWD_R = 37  # r^3 floats must fit in shared memory for the cell-plan kernel
+    MAX_FAST_DEVOX_BWD_R = 256  # 24-bit cell ids in the cell plan (r <= 37: plane in shared memory, above: global atomics)
 
     @staticmethod
     def trilinear_devoxelize_backward_coords(grad_y, coords, r):

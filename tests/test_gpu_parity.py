@@ -665,8 +665,16 @@ def test_resolution_64_plane_outside_shared_memory(be, oracle):
     assert_equal(host(inds), oi, "inds"); assert_equal(host(wgts), ow, "wgts"); assert_close(host(outs), oo, "outs")
     from pcfm.functional import trilinear_devoxelize
     v = cu(vox).view(1, 2, res, res, res).requires_grad_(True)
-    trilinear_devoxelize(v, cu(coords), res, True).backward(cu(gy))       # r > 37: generic backward entry
-    assert_close(host(v.grad).reshape(1, 2, -1), oracle.trilinear_devoxelize_backward(gy, oi, ow, res), "grad", atol_frac=1e-5)
+    trilinear_devoxelize(v, cu(coords), res, True).backward(cu(gy))       # r > 37: cell plan + global atomics
+    want = oracle.trilinear_devoxelize_backward(gy, oi, ow, res)
+    assert_close(host(v.grad).reshape(1, 2, -1), want, "grad", atol_frac=1e-5)
+    assert_close(host(be.pvcnn.trilinear_devoxelize_backward(cu(gy), inds, wgts, res)), want, "grad (generic entry)",
+                 atol_frac=1e-5)
+    # a cloud too big for shared memory on a grid too big for shared memory: rows read through L2 as well
+    cb, vb, gb, _ = cases.devox_case(seed=84, b=1, c=2, n=70000, res=40)
+    _, ib, wb = be.pvcnn.trilinear_devoxelize_forward(40, True, cu(cb), cu(vb))
+    assert_close(host(be.pvcnn.trilinear_devoxelize_backward_coords(cu(gb), cu(cb), 40)),
+                 oracle.trilinear_devoxelize_backward(gb, host(ib), host(wb), 40), "grad r=40 N=70000", atol_frac=1e-5)
     feat, c2, _ = cases.voxel_case(seed=82, b=1, c=2, n=3000, res=64)
     vc, _ = gpu_voxel_coords(c2, 64)
     out, ind, cnt = be.pvcnn.avg_voxelize_forward(cu(feat), vc, 64)
