@@ -16,6 +16,7 @@ Also measured and reported in the same JSON line:
   e2e           the same chains through the autograd operator API with HOST (pinned) inputs and outputs
   cpu_baseline  the same ops in stock PyTorch on the host cores (oracle/torch_cpu.py), bounded sample
   allpairs      all-pairs Chamfer / EMD cloud-pairs/s (config 4 shapes), rows sharded over the N ranks
+  pvconv_modules  the same 6 PVConv blocks as nn.Modules (cuDNN Conv3d / BatchNorm included), forward + backward
 
 --impl reference runs only the PyTorch-CPU arm (rank 0) and prints the same line shape.
 """
@@ -331,6 +332,51 @@ def run_ours(args):
                   "in and out every step, uploads / kernels / downloads on three streams"}
     del h_in, h_out
 
+    # ---------------- module level: the PVConv pyramid of ContextNet, forward + backward, cuDNN included ----------------
+    module = None
+    if not args.skip_module:
+        try:
+            from pcfm.nn import PVConv, SharedMLP
+            torch.manual_seed(0)
+            layers, cin = [], 64
+            for (c, r) in STAGES:                      # models.py:372-386: SharedMLP projection, then PVConv blocks
+                if c != cin:
+                    layers.append(SharedMLP(cin, [c]))
+                    cin = c
+                layers.append(PVConv(c, c, 3, r, with_se=True, normalize=True, eps=1e-6))
+            net = torch.nn.ModuleList(layers).to(dev).train()
+            mf = torch.randn(B, 64, NPTS, device=dev, generator=g).requires_grad_(True)
+            mc = torch.randn(B, 3, NPTS, device=dev, generator=g)
+
+            def module_step():
+                f, c = mf, mc.clone()              # a new coords tensor every step: no memo hit across steps
+                for layer in net:
+                    f, c = layer((f, c))
+                f.square().mean().backward()
+
+            def time_module(n_it):
+                module_step(); module_step()
+                torch.cuda.synchronize()
+                m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                _lib.reset_launch_count()
+                m0.record()
+                for _ in range(n_it):
+                    module_step()
+                m1.record()
+                torch.cuda.synchronize()
+                return m0.elapsed_time(m1) / n_it, _lib.launch_count() / n_it
+
+            ms_mod, launches_mod = time_module(5)
+            module = {"what": "SharedMLP projections + 6 PVConv blocks (Conv3d/BatchNorm3d/SE through cuDNN/cuBLAS, TF32 "
+                              "conv default) of ContextNet on ONE shared coords tensor, forward + backward, B=8, N=20000",
+                      "ms_fwd_bwd": ms_mod, "mpts_per_s": B * NPTS * len(STAGES) / ms_mod / 1e3,
+                      "pcfm_launches_per_step": launches_mod,
+                      "primitive_share": round(ms_per_step / ms_mod, 3)}
+            del net, mf, mc
+            torch.cuda.empty_cache()
+        except Exception as e:  # noqa: BLE001
+            module = {"error": repr(e)}
+
     # ---------------- all-pairs CD / EMD (config 4 shapes), rows sharded over ranks ----------------
     allpairs = None
     try:
@@ -383,7 +429,7 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG, "clocks": clocks,
-                "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "allpairs": allpairs,
+                "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "allpairs": allpairs, "pvconv_modules": module,
                 "lib": _lib.build_info()}
         print(json.dumps(line))
     if world > 1:
@@ -398,6 +444,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-allpairs", action="store_true", help="profiling runs: PVConv primitives only")
+    ap.add_argument("--skip-module", action="store_true", help="skip the module-level (cuDNN included) measurement")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
