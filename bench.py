@@ -157,7 +157,7 @@ def run_reference_arm(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG,
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    print(json.dumps(line), file=_JSON_OUT, flush=True)
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -172,8 +172,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep stdout to the single JSON line (NCCL prints its version there)
         dist.init_process_group("nccl", device_id=dev)
     import pcfm  # noqa: F401
     from pcfm import _lib, backend as be
@@ -431,12 +429,25 @@ def run_ours(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "allpairs": allpairs, "pvconv_modules": module,
                 "lib": _lib.build_info()}
-        print(json.dumps(line))
+        print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = sys.stdout
+
+
+def _reserve_stdout():
+    """stdout carries exactly ONE JSON line: everything else that libraries print there (NCCL's version banner,
+    NCCL_DEBUG output, cpp_extension chatter) is sent to stderr by pointing fd 1 at fd 2 for the rest of the run."""
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
 def main():
+    _reserve_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)

@@ -340,12 +340,7 @@ int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, i
   int rc = cellplan_build(coords, nullptr, r, ind, b, n, t, cnt, &plan, &ws, st);
   if (rc || c == 0) return rc;
   dim3 grid(c, b);
-  static bool attr_set = false;
-  if (!attr_set) {
-    PCFM_CUDA(cudaFuncSetAttribute(vox_fwd_cell_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kMaxStageFloats * sizeof(float))));
-    attr_set = true;
-  }
+  PCFM_CUDA(allow_dyn_smem((const void*)vox_fwd_cell_kernel<true>, (int)(kMaxStageFloats * sizeof(float))));
   if (n <= kMaxStageFloats)
     PCFM_CUDA(launch_dependent(vox_fwd_cell_kernel<true>, grid, dim3(1024), (size_t)n * sizeof(float), st, plan.pdl,
                                features, plan.cells, plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c,
@@ -383,16 +378,12 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
   CellPlan plan;
   int rc = cellplan_build(nullptr, coords, r, nullptr, b, n, t, nullptr, &plan, &ws, st);
   if (rc) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)kSmemLimit));
-    PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)kSmemLimit));
-    PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)kSmemLimit));
-    attr_set = true;
-  }
+  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kSmemLimit));
+  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kSmemLimit));
+  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kSmemLimit));
   dim3 grid(c, b);
   const bool row_smem = devox_bwd_smem(n, r, true, plane_smem) <= kSmemLimit;
   const size_t smem = devox_bwd_smem(n, r, row_smem, plane_smem);

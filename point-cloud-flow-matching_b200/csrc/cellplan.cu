@@ -451,14 +451,8 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
   const int tq = (cdiv(cdiv(t, 32), kCl)) * 32;  // cells per CTA of the cluster
   const size_t tab_bytes = (size_t)tq * sizeof(int);
   if (g_opt_plan == 0 && n > 0 && n <= kFusedMaxPoints && tab_bytes <= kFusedMaxTable) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      PCFM_CUDA(cudaFuncSetAttribute(cp_cluster_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kFusedMaxTable));
-      PCFM_CUDA(cudaFuncSetAttribute(cp_cluster_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)kFusedMaxTable));
-      attr_set = true;
-    }
+    PCFM_CUDA(allow_dyn_smem((const void*)cp_cluster_kernel<true>, (int)kFusedMaxTable));
+    PCFM_CUDA(allow_dyn_smem((const void*)cp_cluster_kernel<false>, (int)kFusedMaxTable));
     if (tri)
       cp_cluster_kernel<true><<<b * kCl, kPlanThreads, tab_bytes, st>>>(
           nullptr, float_coords, r, nullptr, n, t, tq, plan->light_max, plan->chunk, nullptr, rank, plan->cells, plan->slot0,

@@ -284,12 +284,7 @@ int pcfm_chamfer3d_allpairs(const float* s, const float* r, int ns, int nr, int 
   if ((long long)ns * nr > 0x7fffffffLL) return PCFM_E_BADARG;
   if (ns == 0 || nr == 0) return 0;
   if (!s || !r || !cd) return PCFM_E_BADARG;
-  static bool attr_set = false;
-  if (!attr_set) {
-    PCFM_CUDA(cudaFuncSetAttribute(chamfer_allpairs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (kApMaxM + 2) * 20));
-    attr_set = true;
-  }
+  PCFM_CUDA(allow_dyn_smem((const void*)chamfer_allpairs_kernel, (kApMaxM + 2) * 20));
   const size_t smem = (size_t)((m + 1) & ~1) * 20;
   chamfer_allpairs_kernel<<<(unsigned)((long long)ns * nr), kApThreads, smem, (cudaStream_t)stream>>>(
       s, r, nr, n, m, cd);

@@ -25,6 +25,9 @@ extern int g_opt_gather_bwd;    // 0 = gather backward with atomics (like the re
 extern int g_opt_plan;          // 0 = fused cell-plan build when it fits, 1 = always the multi-kernel build
 extern int g_num_sms;           // cached SM count of the current device (148 on B200)
 int num_sms();
+// cudaFuncSetAttribute(func, MaxDynamicSharedMemorySize, bytes) once per (kernel, device): function attributes are
+// per device, so a process that drives several GPUs must set them on each one
+cudaError_t allow_dyn_smem(const void* func, int bytes);
 
 #define PCFM_LAUNCHED()                                   \
   do {                                                    \

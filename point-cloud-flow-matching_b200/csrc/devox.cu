@@ -187,13 +187,9 @@ constexpr size_t kDevoxSmemLimit = 227 * 1024 - 512;
 template <int G, int RT, bool PLANE_SMEM, bool IL = false>
 static int launch_devox_t(const float* coords, const float* feat, float* outs, int* inds, float* wgts, int b,
                           int c, int n, int r, int training, cudaStream_t st) {
-  static bool attr_set = false;
   auto kern = devox_fwd_kernel<G, RT, PLANE_SMEM, IL>;
   const size_t smem = PLANE_SMEM ? devox_fwd_smem(G, r) : 0;
-  if (!attr_set) {
-    PCFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDevoxSmemLimit));
-    attr_set = true;
-  }
+  PCFM_CUDA(allow_dyn_smem((const void*)kern, (int)kDevoxSmemLimit));
   dim3 grid(c / G, b);
   // two CTAs per SM when the planes are small (56+ registers: 512 threads each), else one CTA of 1024 threads
   const int threads = (PLANE_SMEM && smem <= 110 * 1024) ? 512 : 1024;

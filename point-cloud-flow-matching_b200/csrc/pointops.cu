@@ -374,13 +374,9 @@ int pcfm_furthest_point_sampling(const float* coords, int b, int n, int m, int* 
     const int per = cdiv(n, kFpsCl);
     dim3 grid(b * kFpsCl);
     if (per > 1024 * 8) {
-      static bool attr_set = false;
       const size_t smem = (size_t)per * 3 * sizeof(float);
-      if (!attr_set) {
-        PCFM_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       16384 * 3 * (int)sizeof(float)));
-        attr_set = true;
-      }
+      PCFM_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     16384 * 3 * (int)sizeof(float)));
       fps_cluster_kernel<16, true><<<grid, 1024, smem, st>>>(coords, n, m, indices);
     } else {
       int nt = 512, ppt = 1;
@@ -398,12 +394,7 @@ int pcfm_furthest_point_sampling(const float* coords, int b, int n, int m, int* 
   }
   const size_t smem = (size_t)n * 4 * sizeof(float);
   if (smem <= (size_t)kMaxStageFloats * sizeof(float)) {
-    static bool attr_set = false;
-    if (!attr_set) {
-      PCFM_CUDA(cudaFuncSetAttribute(fps_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)(kMaxStageFloats * sizeof(float))));
-      attr_set = true;
-    }
+    PCFM_CUDA(allow_dyn_smem((const void*)fps_kernel<true>, (int)(kMaxStageFloats * sizeof(float))));
     fps_kernel<true><<<b, 1024, smem, st>>>(coords, n, m, nullptr, indices);
   } else {
     Workspace ws(workspace, workspace_bytes);

@@ -74,14 +74,9 @@ __global__ void __launch_bounds__(1024, 1)
 template <int MODE, bool ROW_SMEM>
 static int launch_segsum_t(const float* src, const CsrPlan& plan, float* out, int b, int c, int s, int t,
                            int e, cudaStream_t st) {
-  static bool attr_set = false;
   auto kern = row_segsum_kernel<MODE, ROW_SMEM>;
   const size_t smem = ROW_SMEM ? (size_t)s * sizeof(float) : 0;
-  if (!attr_set) {
-    PCFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kMaxStageFloats * sizeof(float))));
-    attr_set = true;
-  }
+  PCFM_CUDA(allow_dyn_smem((const void*)kern, (int)(kMaxStageFloats * sizeof(float))));
   dim3 grid(c, b);
   kern<<<grid, 1024, smem, st>>>(src, plan.start, plan.ssrc, plan.sw, plan.heavy, plan.nheavy, plan.hcap, out, c,
                                  s, t, e, g_opt_stage == 0);
@@ -172,14 +167,9 @@ __global__ void __launch_bounds__(1024, 1)
 template <int K, int G, bool PLANE_SMEM, bool HAS_W>
 static int launch_gather_t(const float* planes, const int* idx, const float* w, float* out, int b, int c,
                            int p, int j, cudaStream_t st) {
-  static bool attr_set = false;
   auto kern = row_gather_kernel<K, G, PLANE_SMEM, HAS_W>;
   const size_t smem = PLANE_SMEM ? (size_t)G * p * sizeof(float) : 0;
-  if (!attr_set) {
-    PCFM_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   (int)(kMaxStageFloats * sizeof(float))));
-    attr_set = true;
-  }
+  PCFM_CUDA(allow_dyn_smem((const void*)kern, (int)(kMaxStageFloats * sizeof(float))));
   dim3 grid(c / G, b);
   kern<<<grid, 1024, smem, st>>>(planes, idx, w, out, c, p, j, g_opt_stage == 0);
   PCFM_LAUNCHED();

@@ -1,6 +1,10 @@
 // runtime.cu — library globals: options, launch counter, build info.
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace pcfm {
@@ -25,6 +29,19 @@ int num_sms() {
       g_num_sms = 148;
   }
   return g_num_sms;
+}
+cudaError_t allow_dyn_smem(const void* func, int bytes) {
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, int> done;  // (kernel, device) -> bytes already allowed
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  std::lock_guard<std::mutex> lock(mu);
+  int& have = done[std::make_pair(func, dev)];
+  if (have >= bytes) return cudaSuccess;
+  e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) have = bytes;
+  return e;
 }
 }  // namespace pcfm
 

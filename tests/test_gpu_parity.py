@@ -768,3 +768,32 @@ def test_random_small_shapes_metrics_and_pointnet_ops(be, oracle):
         oo3, oi3, ow3 = oracle.three_nn_interpolate_forward(pts, host(ctr), cfeat)
         assert_equal(host(i3), oi3, "3nn idx " + tag); assert_equal(host(w3), ow3, "3nn w " + tag)
         assert_close(host(o3), oo3, "3nn out " + tag)
+
+
+def test_two_devices_in_one_process(be, oracle):
+    """Kernel attributes (dynamic shared memory opt-in) are per device: the same process must be able to run the
+    big-shared-memory kernels on a second GPU after it has used the first."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    feat, coords, res = cases.voxel_case(seed=95, b=2, c=4, n=20000, res=32)
+    want = None
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        with torch.cuda.device(dev):
+            c = torch.from_numpy(coords).to(dev)
+            nc = c - c.mean(2, keepdim=True)
+            nc = torch.clamp((nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0) + 0.5) * res, 0, res - 1)
+            vox = torch.round(nc).to(torch.int32).contiguous()
+            f = torch.from_numpy(feat).to(dev)
+            out, ind, cnt = be.pvcnn.avg_voxelize_forward(f, vox, res)
+            outs, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, nc.contiguous(), out)
+            g = be.pvcnn.trilinear_devoxelize_backward_coords(outs, nc.contiguous(), res)
+            gf = be.pvcnn.avg_voxelize_backward(g, ind, cnt)
+            torch.cuda.synchronize(dev)
+            got = [t.cpu().numpy() for t in (out, outs, g, gf)]
+        if want is None:
+            want = got
+            o_out, _, _ = oracle.avg_voxelize_forward(feat, vox.cpu().numpy(), res)
+            assert_close(got[0], o_out, "voxelize on cuda:0")
+        else:
+            for a, b_, name in zip(got, want, ("vox", "devox", "devox bwd", "vox bwd")):
+                assert_close(a, b_, f"{name} on {dev} vs cuda:0", rtol=1e-6, atol_frac=1e-6)
