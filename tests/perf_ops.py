@@ -160,6 +160,19 @@ def main():
                 if rfn is not None:
                     row["ms_reference_cuda"] = round(timeit(rfn, iters=2, warm=1), 3)
                 rows.append(row); print(json.dumps(row), flush=True)
+    if only and "allpairs" in only:
+        # config 4 kernels on a block that fills the GPU several times: 296 x 64 cloud pairs (CD), 296 x 8 (EMD)
+        S = torch.randn(296, 2048, 3, device=dev, generator=g) * 0.3
+        Rr = torch.randn(64, 2048, 3, device=dev, generator=g) * 0.3
+        row = {"op": "chamfer_allpairs", "pairs": 296 * 64, "N": 2048,
+               "ms": round(timeit(lambda: be.chamfer3d_allpairs(S, Rr), iters=args.iters, warm=args.warm), 3)}
+        row["Mpairs_per_s"] = round(row["pairs"] / row["ms"] / 1e3, 4)
+        row["Tevals_per_s"] = round(row["pairs"] * 2048 * 2048 / row["ms"] / 1e9, 3)
+        rows.append(row); print(json.dumps(row), flush=True)
+        row = {"op": "emd_allpairs", "pairs": 296 * 8, "N": 2048,
+               "ms": round(timeit(lambda: be.emd_allpairs(S, Rr[:8]), iters=max(1, args.iters // 3), warm=min(args.warm, 1)), 3)}
+        row["kpairs_per_s"] = round(row["pairs"] / row["ms"], 3)
+        rows.append(row); print(json.dumps(row), flush=True)
     if not only or "chamfer" in only:
         for (b, n, m) in [(32, 2000, 1000), (2, 2048, 2048), (8, 20000, 20000)]:
             a = torch.rand(b, n, 3, device=dev, generator=g); c2 = torch.rand(b, m, 3, device=dev, generator=g)
