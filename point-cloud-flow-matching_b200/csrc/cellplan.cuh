@@ -20,7 +20,7 @@ namespace pcfm {
 constexpr int kLightCap = 64;      // upper bound of light_max (<= 255: 8-bit count field of CellPlan::cells)
 constexpr int kLightMaxMean = 64;
 constexpr int kLightMaxTri = 64;
-constexpr int kHeavyChunk = 256;   // trilinear plans: a heavy cell is listed as pieces of at most this many records, so no
+constexpr int kHeavyChunk = 512;   // trilinear plans: a heavy cell is listed as pieces of at most this many records, so no
                                   // single warp owns a 2000-point cell (the pieces are combined with atomics anyway)
 constexpr int kSortMax = 16;   // light cells up to this size keep their records in ascending point order
 constexpr int kMetaInts = 4;   // per batch element: [0] end of the light list (multiple of 32), [1] heavy cells

@@ -67,7 +67,16 @@ static inline cudaError_t launch_dependent(void (*kern)(KArgs...), dim3 grid, di
 struct Workspace {
   char* base;
   size_t cap, off;
-  Workspace(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0) {}
+  // blocks are handed out on 256-byte boundaries whatever the alignment of the caller's buffer (the *_workspace()
+  // sizes include that slack)
+  Workspace(void* p, size_t bytes) : base((char*)p), cap(bytes), off(0) {
+    const size_t mis = (size_t)((uintptr_t)p & 255);
+    if (p && mis) {
+      const size_t skip = 256 - mis;
+      if (skip >= bytes) { base = nullptr; cap = 0; }
+      else { base += skip; cap -= skip; }
+    }
+  }
   template <typename T>
   T* take(size_t count) {
     size_t bytes = align256(count * sizeof(T));

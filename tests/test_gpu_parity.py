@@ -770,6 +770,33 @@ def test_random_small_shapes_metrics_and_pointnet_ops(be, oracle):
         assert_close(host(o3), oo3, "3nn out " + tag)
 
 
+def test_unaligned_workspace_pointer(be):
+    """The C ABI takes any workspace pointer: blocks are carved on 256-byte boundaries inside it (the *_workspace()
+    sizes include the slack)."""
+    from pcfm import _lib
+    feat, coords, res = cases.voxel_case(seed=96, b=2, c=4, n=3000, res=16)
+    vox, nc = gpu_voxel_coords(coords, res)
+    f = cu(feat)
+    want = be.pvcnn.avg_voxelize_forward(f, vox, res)
+    b, c, n = f.shape
+    s = res ** 3
+    out = torch.empty(b, c, s, device="cuda")
+    ind = torch.empty(b, n, dtype=torch.int32, device="cuda")
+    cnt = torch.empty(b, s, dtype=torch.int32, device="cuda")
+    nb = _lib.lib.pcfm_avg_voxelize_forward_workspace(b, c, n, res)
+    ws = torch.empty(nb + 8, dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    rc = _lib.lib.pcfm_avg_voxelize_forward(f.data_ptr(), vox.data_ptr(), b, c, n, res, out.data_ptr(), ind.data_ptr(),
+                                            cnt.data_ptr(), ws.data_ptr() + 4, nb, st)
+    assert rc == 0
+    assert torch.equal(ind, want[1]) and torch.equal(cnt, want[2])
+    assert_close(host(out), host(want[0]), "out with an unaligned workspace")
+    # a workspace that is too small is reported, not overrun
+    rc = _lib.lib.pcfm_avg_voxelize_forward(f.data_ptr(), vox.data_ptr(), b, c, n, res, out.data_ptr(), ind.data_ptr(),
+                                            cnt.data_ptr(), ws.data_ptr(), 1024, st)
+    assert rc != 0
+
+
 def test_two_devices_in_one_process(be, oracle):
     """Kernel attributes (dynamic shared memory opt-in) are per device: the same process must be able to run the
     big-shared-memory kernels on a second GPU after it has used the first."""
