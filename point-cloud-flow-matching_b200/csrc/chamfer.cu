@@ -133,6 +133,27 @@ __global__ void __launch_bounds__(256)
 // the float bit pattern per warp; non-negative floats order like unsigned ints).  No indices are needed for
 // the metric, so the inner loop is 3 FADD + FMUL + 2 FFMA + 2 FMNMX per pair of points.
 // =================================================================================================
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2), each lane rounded exactly like the scalar instruction ----
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// sq3() of common.cuh on two lanes: FMUL2(dy,dy); FFMA2(dx,dx,.); FFMA2(dz,dz,.) -> bit patterns of the two results
+__device__ __forceinline__ void sq3x2(unsigned long long dx, unsigned long long dy, unsigned long long dz,
+                                      unsigned& lo, unsigned& hi) {
+  unsigned long long t;
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
+}
+
 // 128 threads x 16 own points (2048 rows per sweep).  64 x 32 needs 168 registers per thread: 3 warps per scheduler,
 // 68 % issue-active with fixed-latency "wait" stalls (ncu); measured 0.82 / 1.04 / 0.96 M pairs/s for 64x32 / 128x16 /
 // 256x8 (the column-min reduction per warp grows as the tile gets narrower).
@@ -142,7 +163,8 @@ constexpr int kApMaxM = 8192;
 
 // Minima are taken on the IEEE bit patterns with the 3-input integer min (VIMNMX3): squared distances are >= +0,
 // where unsigned order == float order, so two distances are folded per instruction for the row side and two for
-// the column side: 3 FADD + FMUL + 2 FFMA + 1 VIMNMX3 = 7 issue slots per evaluated pair of points.
+// the column side.  With the arithmetic packed two rows per instruction (below): 4 issue slots per evaluated pair of
+// points, 6 cycles of the fp32 pipe.
 __global__ void __launch_bounds__(kApThreads)
     chamfer_allpairs_kernel(const float* __restrict__ s, const float* __restrict__ rr, int nr, int n, int m,
                             float* __restrict__ cd) {
@@ -169,28 +191,39 @@ __global__ void __launch_bounds__(kApThreads)
   __syncthreads();
   float rowsum = 0.f;
   for (int base = 0; base < n; base += kApThreads * kApRows) {
-    float ax[kApRows], ay[kApRows], az[kApRows];
+    // rows are held in PAIRS (r, r+1) packed in 64-bit registers: the subtractions, the square and the two FMAs of a
+    // distance are issued as FADD2 / FMUL2 / FFMA2 (sm_100 packed fp32: two IEEE-exact lanes per instruction), which
+    // halves the issue slots of the arithmetic: 3 + 1 + 2 packed + 2 VIMNMX3 per TWO distances = 4 slots each
+    unsigned long long ax[kApRows / 2], ay[kApRows / 2], az[kApRows / 2];
     unsigned rmin[kApRows];
 #pragma unroll
-    for (int r = 0; r < kApRows; ++r) {
-      const int row = base + r * kApThreads + threadIdx.x;
-      const bool v = row < n;
-      // rows past the end sit at +inf: their distances are +inf (or NaN -> masked below) and never lower a minimum
-      ax[r] = v ? a[(long long)row * 3 + 0] : pos_inf();
-      ay[r] = v ? a[(long long)row * 3 + 1] : pos_inf();
-      az[r] = v ? a[(long long)row * 3 + 2] : pos_inf();
-      rmin[r] = 0x7f800000u;
+    for (int r = 0; r < kApRows; r += 2) {
+      float x[2], y[2], z[2];
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int row = base + (r + h) * kApThreads + threadIdx.x;
+        const bool v = row < n;
+        // rows past the end sit at +inf: their distances are +inf (or NaN, whose bit pattern is above +inf's) and
+        // never lower a minimum
+        x[h] = v ? a[(long long)row * 3 + 0] : pos_inf();
+        y[h] = v ? a[(long long)row * 3 + 1] : pos_inf();
+        z[h] = v ? a[(long long)row * 3 + 2] : pos_inf();
+        rmin[r + h] = 0x7f800000u;
+      }
+      ax[r / 2] = pack2(x[0], x[1]);
+      ay[r / 2] = pack2(y[0], y[1]);
+      az[r / 2] = pack2(z[0], z[1]);
     }
     for (int k = 0; k < m2; k += 2) {
       const float4 q0 = col[k], q1 = col[k + 1];
+      const unsigned long long q0x = pack2(q0.x, q0.x), q0y = pack2(q0.y, q0.y), q0z = pack2(q0.z, q0.z);
+      const unsigned long long q1x = pack2(q1.x, q1.x), q1y = pack2(q1.y, q1.y), q1z = pack2(q1.z, q1.z);
       unsigned cm0 = 0x7f800000u, cm1 = 0x7f800000u;
 #pragma unroll
       for (int r = 0; r < kApRows; r += 2) {
-        // inf - inf = NaN only when a pad row meets the pad column: fminf(.., inf) maps it back to +inf
-        const unsigned d00 = __float_as_uint(sq3(q0.x - ax[r], q0.y - ay[r], q0.z - az[r]));
-        const unsigned d01 = __float_as_uint(sq3(q1.x - ax[r], q1.y - ay[r], q1.z - az[r]));
-        const unsigned d10 = __float_as_uint(sq3(q0.x - ax[r + 1], q0.y - ay[r + 1], q0.z - az[r + 1]));
-        const unsigned d11 = __float_as_uint(sq3(q1.x - ax[r + 1], q1.y - ay[r + 1], q1.z - az[r + 1]));
+        unsigned d00, d10, d01, d11;  // d<row half><column>
+        sq3x2(sub2(q0x, ax[r / 2]), sub2(q0y, ay[r / 2]), sub2(q0z, az[r / 2]), d00, d10);
+        sq3x2(sub2(q1x, ax[r / 2]), sub2(q1y, ay[r / 2]), sub2(q1z, az[r / 2]), d01, d11);
         rmin[r] = __vimin3_u32(rmin[r], d00, d01);
         rmin[r + 1] = __vimin3_u32(rmin[r + 1], d10, d11);
         cm0 = __vimin3_u32(cm0, d00, d10);
