@@ -13,17 +13,43 @@ constexpr int kChChunk = 2048;  // points of the other cloud per shared-memory c
 
 __device__ __forceinline__ float pos_inf() { return __int_as_float(0x7f800000); }
 
+// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2), each lane rounded exactly like the scalar instruction ----
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+// sq3() of common.cuh on two lanes: FMUL2(dy,dy); FFMA2(dx,dx,.); FFMA2(dz,dz,.) -> bit patterns of the two results
+__device__ __forceinline__ void sq3x2(unsigned long long dx, unsigned long long dy, unsigned long long dz,
+                                      unsigned& lo, unsigned& hi) {
+  unsigned long long t;
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
+}
+
+
 // one direction: for every point of `a` ([B,n,3]) the nearest point of `o` ([B,m,3])
 template <int RA>
 __global__ void __launch_bounds__(kChThreads)
     chamfer_nn_kernel(const float* __restrict__ a, const float* __restrict__ o, int n, int m,
                       float* __restrict__ dist, int* __restrict__ idx) {
-  __shared__ float4 buf[kChChunk];
+  // the other cloud in SoA groups of four: one LDS.128 per coordinate yields two natural register PAIRS of columns,
+  // so the distance arithmetic issues as packed FADD2 / FMUL2 / FFMA2 (two columns per instruction, lanes rounded
+  // exactly like the scalar sq3)
+  __shared__ __align__(16) float bx[kChChunk], by[kChChunk], bz[kChChunk];
   const int b = blockIdx.y;
   const float* ab = a + (long long)b * n * 3;
   const float* ob = o + (long long)b * m * 3;
   const int row0 = blockIdx.x * (kChThreads * RA) + threadIdx.x;
   float ax[RA], ay[RA], az[RA], best[RA];
+  unsigned long long axp[RA], ayp[RA], azp[RA];
   int bk[RA];
 #pragma unroll
   for (int r = 0; r < RA; ++r) {
@@ -32,6 +58,9 @@ __global__ void __launch_bounds__(kChThreads)
     ax[r] = v ? ab[(long long)i * 3 + 0] : 0.f;
     ay[r] = v ? ab[(long long)i * 3 + 1] : 0.f;
     az[r] = v ? ab[(long long)i * 3 + 2] : 0.f;
+    axp[r] = pack2(ax[r], ax[r]);
+    ayp[r] = pack2(ay[r], ay[r]);
+    azp[r] = pack2(az[r], az[r]);
     best[r] = pos_inf();
     bk[r] = 0;
   }
@@ -40,25 +69,24 @@ __global__ void __launch_bounds__(kChThreads)
     const int len4 = (len + 3) & ~3;
     __syncthreads();
     for (int k = threadIdx.x; k < len4; k += kChThreads) {
-      float4 q;
-      if (k < len) {
-        const float* p = ob + (long long)(k2 + k) * 3;
-        q = make_float4(p[0], p[1], p[2], 0.f);
-      } else {
-        q = make_float4(pos_inf(), pos_inf(), pos_inf(), 0.f);  // padding: distance +inf, never a strict minimum
-      }
-      buf[k] = q;
+      const bool v = k < len;  // padding: distance +inf, never a strict minimum
+      const float* p = ob + (long long)(k2 + (v ? k : 0)) * 3;
+      bx[k] = v ? p[0] : pos_inf();
+      by[k] = v ? p[1] : pos_inf();
+      bz[k] = v ? p[2] : pos_inf();
     }
     __syncthreads();
     for (int k = 0; k < len4; k += 4) {
-      const float4 q0 = buf[k], q1 = buf[k + 1], q2 = buf[k + 2], q3 = buf[k + 3];
+      const ulonglong2 qx = *reinterpret_cast<const ulonglong2*>(bx + k);  // (x0,x1) (x2,x3)
+      const ulonglong2 qy = *reinterpret_cast<const ulonglong2*>(by + k);
+      const ulonglong2 qz = *reinterpret_cast<const ulonglong2*>(bz + k);
 #pragma unroll
       for (int r = 0; r < RA; ++r) {
-        const float d0 = sq3(q0.x - ax[r], q0.y - ay[r], q0.z - az[r]);
-        const float d1 = sq3(q1.x - ax[r], q1.y - ay[r], q1.z - az[r]);
-        const float d2 = sq3(q2.x - ax[r], q2.y - ay[r], q2.z - az[r]);
-        const float d3 = sq3(q3.x - ax[r], q3.y - ay[r], q3.z - az[r]);
-        const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+        unsigned u0, u1, u2, u3;
+        sq3x2(sub2(qx.x, axp[r]), sub2(qy.x, ayp[r]), sub2(qz.x, azp[r]), u0, u1);
+        sq3x2(sub2(qx.y, axp[r]), sub2(qy.y, ayp[r]), sub2(qz.y, azp[r]), u2, u3);
+        const float m4 = fminf(fminf(__uint_as_float(u0), __uint_as_float(u1)),
+                               fminf(__uint_as_float(u2), __uint_as_float(u3)));
         if (m4 < best[r]) {  // strict: the first group of four that reaches the minimum wins
           best[r] = m4;
           bk[r] = k2 + k;
@@ -133,27 +161,6 @@ __global__ void __launch_bounds__(256)
 // the float bit pattern per warp; non-negative floats order like unsigned ints).  No indices are needed for
 // the metric, so the inner loop is 3 FADD + FMUL + 2 FFMA + 2 FMNMX per pair of points.
 // =================================================================================================
-// ---- packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2), each lane rounded exactly like the scalar instruction ----
-__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ unsigned long long sub2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-// sq3() of common.cuh on two lanes: FMUL2(dy,dy); FFMA2(dx,dx,.); FFMA2(dz,dz,.) -> bit patterns of the two results
-__device__ __forceinline__ void sq3x2(unsigned long long dx, unsigned long long dy, unsigned long long dz,
-                                      unsigned& lo, unsigned& hi) {
-  unsigned long long t;
-  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
-  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
-  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
-  asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(t));
-}
-
 // 128 threads x 16 own points (2048 rows per sweep).  64 x 32 needs 168 registers per thread: 3 warps per scheduler,
 // 68 % issue-active with fixed-latency "wait" stalls (ncu); measured 0.82 / 1.04 / 0.96 M pairs/s for 64x32 / 128x16 /
 // 256x8 (the column-min reduction per warp grows as the tile gets narrower).
