@@ -275,6 +275,7 @@ constexpr int kNnTile = 2048;
 __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ points,
                                                        const float* __restrict__ centers, int n, int m,
                                                        float* __restrict__ weights, int* __restrict__ indices) {
+  griddep_launch_dependents();  // the interpolation gather behind this kernel may start staging its planes
   __shared__ float cx[kNnTile], cy[kNnTile], cz[kNnTile];
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,7 +419,7 @@ int pcfm_three_nn_interpolate_forward(const float* points, const float* centers,
   PCFM_LAUNCHED();
   if (c == 0) return 0;
   if (!centers_features || !out || m == 0) return PCFM_E_BADARG;
-  return launch_row_gather(3, centers_features, idx, wgt, out, b, c, m, n, st);
+  return launch_row_gather(3, centers_features, idx, wgt, out, b, c, m, n, st, true);  // three_nn_kernel releases it early
 }
 
 }  // extern "C"

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(1024, 1)
     __syncthreads();
     stage_floats(smem, pg, G * P, &bar, 0, use_tma != 0);
   }
+  griddep_wait();  // the planes are an input of the operator; idx / w may come from the previous kernel (PDL)
   const int* ib = idx + (long long)b * K * J;
   const float* wb = HAS_W ? w + (long long)b * K * J : nullptr;
   float* ob = out + ((long long)b * C + c0) * J;
@@ -166,12 +167,13 @@ __global__ void __launch_bounds__(1024, 1)
 
 template <int K, int G, bool PLANE_SMEM, bool HAS_W>
 static int launch_gather_t(const float* planes, const int* idx, const float* w, float* out, int b, int c,
-                           int p, int j, cudaStream_t st) {
+                           int p, int j, cudaStream_t st, bool dependent) {
   auto kern = row_gather_kernel<K, G, PLANE_SMEM, HAS_W>;
   const size_t smem = PLANE_SMEM ? (size_t)G * p * sizeof(float) : 0;
   PCFM_CUDA(allow_dyn_smem((const void*)kern, (int)(kMaxStageFloats * sizeof(float))));
   dim3 grid(c / G, b);
-  kern<<<grid, 1024, smem, st>>>(planes, idx, w, out, c, p, j, g_opt_stage == 0);
+  PCFM_CUDA(launch_dependent(kern, grid, dim3(1024), smem, st, dependent && g_opt_pdl != 0, planes, idx, w, out, c, p,
+                             j, (int)(g_opt_stage == 0)));
   PCFM_LAUNCHED();
   return 0;
 }
@@ -187,23 +189,25 @@ int pick_group(int b, int c, int p) {
 
 template <int K, bool HAS_W>
 static int launch_gather_k(const float* planes, const int* idx, const float* w, float* out, int b, int c,
-                           int p, int j, cudaStream_t st) {
+                           int p, int j, cudaStream_t st, bool dep) {
   switch (pick_group(b, c, p)) {
-    case 0: return launch_gather_t<K, 1, false, HAS_W>(planes, idx, w, out, b, c, p, j, st);
-    case 8: return launch_gather_t<K, 8, true, HAS_W>(planes, idx, w, out, b, c, p, j, st);
-    case 4: return launch_gather_t<K, 4, true, HAS_W>(planes, idx, w, out, b, c, p, j, st);
-    case 2: return launch_gather_t<K, 2, true, HAS_W>(planes, idx, w, out, b, c, p, j, st);
-    default: return launch_gather_t<K, 1, true, HAS_W>(planes, idx, w, out, b, c, p, j, st);
+    case 0: return launch_gather_t<K, 1, false, HAS_W>(planes, idx, w, out, b, c, p, j, st, dep);
+    case 8: return launch_gather_t<K, 8, true, HAS_W>(planes, idx, w, out, b, c, p, j, st, dep);
+    case 4: return launch_gather_t<K, 4, true, HAS_W>(planes, idx, w, out, b, c, p, j, st, dep);
+    case 2: return launch_gather_t<K, 2, true, HAS_W>(planes, idx, w, out, b, c, p, j, st, dep);
+    default: return launch_gather_t<K, 1, true, HAS_W>(planes, idx, w, out, b, c, p, j, st, dep);
   }
 }
 
+// dependent: the previous kernel on the stream (which produced idx / w) has called griddep_launch_dependents(), so
+// this one may stage its planes while that kernel is still running
 int launch_row_gather(int k, const float* planes, const int* idx, const float* w, float* out, int b, int c,
-                      int p, int j, cudaStream_t st) {
+                      int p, int j, cudaStream_t st, bool dependent) {
   if (b <= 0 || c <= 0 || j <= 0) return 0;
   if (p <= 0) return PCFM_E_BADARG;
-  if (k == 1) return w ? launch_gather_k<1, true>(planes, idx, w, out, b, c, p, j, st)
-                       : launch_gather_k<1, false>(planes, idx, nullptr, out, b, c, p, j, st);
-  if (k == 3 && w) return launch_gather_k<3, true>(planes, idx, w, out, b, c, p, j, st);
+  if (k == 1) return w ? launch_gather_k<1, true>(planes, idx, w, out, b, c, p, j, st, dependent)
+                       : launch_gather_k<1, false>(planes, idx, nullptr, out, b, c, p, j, st, dependent);
+  if (k == 3 && w) return launch_gather_k<3, true>(planes, idx, w, out, b, c, p, j, st, dependent);
   return PCFM_E_BADARG;
 }
 
@@ -214,6 +218,7 @@ int launch_row_gather(int k, const float* planes, const int* idx, const float* w
 __global__ void __launch_bounds__(256) point_rcp_kernel(const int* __restrict__ ind,
                                                         const int* __restrict__ cnt, int n, int s,
                                                         float* __restrict__ rcp) {
+  griddep_launch_dependents();  // the gather kernel behind this one may start staging its planes
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -312,7 +317,7 @@ int pcfm_avg_voxelize_backward(const float* grad_y, const int* ind, const int* c
   dim3 grid(cdiv(n, 256), b);
   point_rcp_kernel<<<grid, 256, 0, st>>>(ind, cnt, n, s, rcp);
   PCFM_LAUNCHED();
-  return launch_row_gather(1, grad_y, ind, rcp, grad_x, b, c, s, n, st);
+  return launch_row_gather(1, grad_y, ind, rcp, grad_x, b, c, s, n, st, true);
 }
 
 // ---------------------------------------------------------------------------------------------

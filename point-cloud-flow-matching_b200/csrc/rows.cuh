@@ -22,7 +22,7 @@ int launch_row_segsum(SegMode mode, const float* src, const CsrPlan& plan, float
 
 // K in {1,3}; w may be nullptr (weights 1, K must be 1).  planes [B,C,P], idx [B,K,J], out [B,C,J].
 int launch_row_gather(int k, const float* planes, const int* idx, const float* w, float* out, int b, int c,
-                      int p, int j, cudaStream_t st);
+                      int p, int j, cudaStream_t st, bool dependent = false);
 
 // channels per CTA for plane-staging kernels (0 = plane does not fit in shared memory)
 int pick_group(int b, int c, int p);
