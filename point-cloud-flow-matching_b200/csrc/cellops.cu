@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(1024, 2)
     if (bulk > 0) mbar_wait(&bar, 0);
   }
   griddep_wait();   // everything above is independent of the plan (PDL: overlaps the plan kernel)
+  griddep_launch_dependents();  // chained PDL: the next kernel on the stream may be scheduled behind this one
   __syncthreads();  // row visible; zero stores ordered before the sums below (same CTA)
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
@@ -171,6 +172,7 @@ __global__ void __launch_bounds__(1024, 1)
     if (bulk > 0) mbar_wait(&bar, 0);
   }
   griddep_wait();  // everything above is independent of the plan (PDL: overlaps the plan kernel)
+  griddep_launch_dependents();  // chained PDL: the next kernel on the stream may be scheduled behind this one
   __syncthreads();
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;

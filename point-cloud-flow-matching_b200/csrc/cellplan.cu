@@ -236,6 +236,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
                       int* __restrict__ rank, int* __restrict__ cells, int* __restrict__ slot0,
                       int* __restrict__ meta, int* __restrict__ heavy, void* __restrict__ rec, int lcap, int hcap,
                       int rcap) {
+  griddep_wait();               // chained PDL: this kernel may itself have started before its predecessor finished
   griddep_launch_dependents();  // the consumer kernel may start staging its rows now; it waits before reading the plan
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ int tab[];  // [tq] this CTA's share of the per-cell table
@@ -453,14 +454,17 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
   if (g_opt_plan == 0 && n > 0 && n <= kFusedMaxPoints && tab_bytes <= kFusedMaxTable) {
     PCFM_CUDA(allow_dyn_smem((const void*)cp_cluster_kernel<true>, (int)kFusedMaxTable));
     PCFM_CUDA(allow_dyn_smem((const void*)cp_cluster_kernel<false>, (int)kFusedMaxTable));
+    const bool chain = g_opt_pdl >= 2;  // see launch_dependent(): overlap the tail of the previous kernel on the stream
     if (tri)
-      cp_cluster_kernel<true><<<b * kCl, kPlanThreads, tab_bytes, st>>>(
-          nullptr, float_coords, r, nullptr, n, t, tq, plan->light_max, plan->chunk, nullptr, rank, plan->cells, plan->slot0,
-          plan->meta, plan->heavy, plan->rec, plan->lcap, plan->hcap, plan->rcap);
+      PCFM_CUDA(launch_dependent(cp_cluster_kernel<true>, dim3(b * kCl), dim3(kPlanThreads), tab_bytes, st, chain,
+                                 (const int*)nullptr, float_coords, r, (int*)nullptr, n, t, tq, plan->light_max,
+                                 plan->chunk, (int*)nullptr, rank, plan->cells, plan->slot0, plan->meta, plan->heavy,
+                                 plan->rec, plan->lcap, plan->hcap, plan->rcap));
     else
-      cp_cluster_kernel<false><<<b * kCl, kPlanThreads, tab_bytes, st>>>(
-          vox_coords, nullptr, r, ind_out, n, t, tq, plan->light_max, plan->chunk, cnt, rank, plan->cells, plan->slot0,
-          plan->meta, plan->heavy, plan->rec, plan->lcap, plan->hcap, plan->rcap);
+      PCFM_CUDA(launch_dependent(cp_cluster_kernel<false>, dim3(b * kCl), dim3(kPlanThreads), tab_bytes, st, chain,
+                                 vox_coords, (const float*)nullptr, r, ind_out, n, t, tq, plan->light_max, plan->chunk,
+                                 cnt, rank, plan->cells, plan->slot0, plan->meta, plan->heavy, plan->rec, plan->lcap,
+                                 plan->hcap, plan->rcap));
     PCFM_LAUNCHED();
     plan->pdl = g_opt_pdl != 0;
     return 0;

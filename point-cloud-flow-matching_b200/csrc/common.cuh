@@ -19,7 +19,9 @@ extern int g_opt_devox_bwd;     // see pcfm_set_option
 extern int g_opt_vox_fwd;
 extern int g_opt_stage;
 extern int g_opt_devox_il;      // 1 = channel-interleaved planes in devoxelize forward when G >= 4 (default)
-extern int g_opt_pdl;           // 1 = row kernels overlap the tail of the fused plan kernel (PDL), 0 = plain launches
+extern int g_opt_pdl;           // programmatic dependent launch: 0 = off, 1 = inside an operator (row kernel behind its
+                                // plan / index kernel), 2 = also between operators (every PVConv kernel waits at its
+                                // top, then releases the kernel behind it: launch + scheduling overlap the previous tail)
 extern int g_opt_fps;           // 0 = cluster FPS (points in registers) when the cloud fits, 1 = one CTA per cloud
 extern int g_opt_gather_bwd;    // 0 = gather backward with atomics (like the reference), 1 = sorted-segment sums
 extern int g_opt_plan;          // 0 = fused cell-plan build when it fits, 1 = always the multi-kernel build

@@ -25,6 +25,8 @@ __global__ void __launch_bounds__(1024, 1)
                      int r_rt, int training, int use_tma) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
+  griddep_wait();  // chained PDL: this kernel may have been scheduled before its predecessor on the stream finished
+  griddep_launch_dependents();
   const int r = RT > 0 ? RT : r_rt;
   const int c0 = blockIdx.x * G, b = blockIdx.y;
   const int r2 = r * r, P = r2 * r;
@@ -193,7 +195,8 @@ static int launch_devox_t(const float* coords, const float* feat, float* outs, i
   dim3 grid(c / G, b);
   // two CTAs per SM when the planes are small (56+ registers: 512 threads each), else one CTA of 1024 threads
   const int threads = (PLANE_SMEM && smem <= 110 * 1024) ? 512 : 1024;
-  kern<<<grid, threads, smem, st>>>(coords, feat, outs, inds, wgts, c, n, r, training, g_opt_stage == 0);
+  PCFM_CUDA(launch_dependent(kern, grid, dim3(threads), smem, st, g_opt_pdl >= 2, coords, feat, outs, inds, wgts, c, n,
+                             r, training, (int)(g_opt_stage == 0)));
   PCFM_LAUNCHED();
   return 0;
 }

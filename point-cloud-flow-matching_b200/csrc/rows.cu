@@ -122,6 +122,7 @@ __global__ void __launch_bounds__(1024, 1)
     stage_floats(smem, pg, G * P, &bar, 0, use_tma != 0);
   }
   griddep_wait();  // the planes are an input of the operator; idx / w may come from the previous kernel (PDL)
+  griddep_launch_dependents();
   const int* ib = idx + (long long)b * K * J;
   const float* wb = HAS_W ? w + (long long)b * K * J : nullptr;
   float* ob = out + ((long long)b * C + c0) * J;
@@ -218,6 +219,7 @@ int launch_row_gather(int k, const float* planes, const int* idx, const float* w
 __global__ void __launch_bounds__(256) point_rcp_kernel(const int* __restrict__ ind,
                                                         const int* __restrict__ cnt, int n, int s,
                                                         float* __restrict__ rcp) {
+  griddep_wait();               // chained PDL: may have started before its predecessor finished
   griddep_launch_dependents();  // the gather kernel behind this one may start staging its planes
   const int b = blockIdx.y;
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -315,7 +317,7 @@ int pcfm_avg_voxelize_backward(const float* grad_y, const int* ind, const int* c
   float* rcp = ws.take<float>((size_t)b * n);
   if (!ws.ok()) return PCFM_E_WORKSPACE;
   dim3 grid(cdiv(n, 256), b);
-  point_rcp_kernel<<<grid, 256, 0, st>>>(ind, cnt, n, s, rcp);
+  PCFM_CUDA(launch_dependent(point_rcp_kernel, grid, dim3(256), 0, st, g_opt_pdl >= 2, ind, cnt, n, s, rcp));
   PCFM_LAUNCHED();
   return launch_row_gather(1, grad_y, ind, rcp, grad_x, b, c, s, n, st, true);
 }

@@ -15,7 +15,7 @@ int g_opt_stage = 0;
 int g_opt_plan = 0;
 int g_opt_gather_bwd = 0;
 int g_opt_fps = 0;
-int g_opt_pdl = 1;
+int g_opt_pdl = 2;
 int g_opt_devox_il = 1;
 int g_num_sms = 0;
 
