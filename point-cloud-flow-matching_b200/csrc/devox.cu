@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(1024, 1)
   // plane stride: r layers + guard; the farthest corner read is r*sx + r*r + r floats from the plane base
   const int sp = PLANE_SMEM ? ((r + 1) * sx + r + 3) & ~3 : P;
   const float* pg = feat + ((long long)b * C + c0) * P;
+  bool bulk_copy = false;
   if (PLANE_SMEM) {
     if (threadIdx.x == 0) {
       mbar_init(&bar, 1);
@@ -41,6 +42,7 @@ __global__ void __launch_bounds__(1024, 1)
     }
     __syncthreads();
     const bool bulk = !IL && use_tma && ((r2 & 3) == 0) && ((((uintptr_t)pg) & 15) == 0);
+    bulk_copy = bulk;
     if (IL) {
       for (int i = threadIdx.x; i < G * sp; i += blockDim.x) smem[i] = 0.f;  // skew + guard voxels
       __syncthreads();
@@ -71,8 +73,6 @@ __global__ void __launch_bounds__(1024, 1)
       const int g = i / guard;
       smem[(size_t)g * sp + (size_t)r * sx + (i - g * guard)] = 0.f;
     }
-    if (bulk) mbar_wait(&bar, 0);
-    __syncthreads();
   }
   const float* cb = coords + (long long)b * 3 * n;
   float* ob = outs + ((long long)b * C + c0) * n;
@@ -80,12 +80,17 @@ __global__ void __launch_bounds__(1024, 1)
   int* ib = inds ? inds + (long long)b * 8 * n : nullptr;
   float* wb = wgts ? wgts + (long long)b * 8 * n : nullptr;
   const float hi = (float)(r - 1);
-  // software pipeline: the coordinates of the next point are requested before the current one is gathered
+  // software pipeline: the coordinates of the next point are requested before the current one is gathered, and those
+  // of the first point while the planes are still landing
   float nx = 0.f, ny = 0.f, nz = 0.f;
   if ((int)threadIdx.x < n) {
     nx = cb[threadIdx.x];
     ny = cb[(long long)threadIdx.x + n];
     nz = cb[(long long)threadIdx.x + 2LL * n];
+  }
+  if (PLANE_SMEM) {
+    if (bulk_copy) mbar_wait(&bar, 0);
+    __syncthreads();
   }
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     // coords are contractually in [0, r-1]; the clamp is a no-op there and keeps every index in range otherwise

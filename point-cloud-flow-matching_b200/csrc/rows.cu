@@ -113,13 +113,21 @@ __global__ void __launch_bounds__(1024, 1)
   __shared__ uint64_t bar;
   const int c0 = blockIdx.x * G, b = blockIdx.y;
   const float* pg = planes + ((long long)b * C + c0) * P;
+  // ---- issue the plane copy (TMA bulk when aligned), do not wait yet ----
+  const int total = G * P;
+  const bool aligned = PLANE_SMEM && use_tma && ((((uintptr_t)pg) & 15) == 0);
+  const int bulk = aligned ? (total & ~3) : 0;
   if (PLANE_SMEM) {
     if (threadIdx.x == 0) {
       mbar_init(&bar, 1);
       fence_mbar_init();
+      if (bulk > 0) {
+        mbar_arrive_expect_tx(&bar, (uint32_t)bulk * 4u);
+        for (uint32_t off = 0; off < (uint32_t)bulk * 4u; off += kBulkChunk)
+          bulk_g2s((char*)smem + off, (const char*)pg + off, min(kBulkChunk, (uint32_t)bulk * 4u - off), &bar);
+      }
     }
-    __syncthreads();
-    stage_floats(smem, pg, G * P, &bar, 0, use_tma != 0);
+    for (int i = bulk + threadIdx.x; i < total; i += blockDim.x) smem[i] = __ldg(pg + i);
   }
   griddep_wait();  // the planes are an input of the operator; idx / w may come from the previous kernel (PDL)
   griddep_launch_dependents();
@@ -127,21 +135,34 @@ __global__ void __launch_bounds__(1024, 1)
   const float* wb = HAS_W ? w + (long long)b * K * J : nullptr;
   float* ob = out + ((long long)b * C + c0) * J;
   const unsigned pmax = (unsigned)(P - 1);
-  // U outputs per thread and iteration: all index / weight loads of the U outputs are issued before the first gather
+  // U outputs per thread and round, software-pipelined: the index / weight loads of round i+1 are in flight while round
+  // i gathers, and those of round 0 while the plane copy lands (the loop was bound by the L2 latency of these loads)
   constexpr int U = (K == 1) ? 4 : 2;
-  for (int j0 = threadIdx.x; j0 < J; j0 += blockDim.x * U) {
-    unsigned id[U][K];
-    float wk[U][K];
+  unsigned id[U][K], idn[U][K];
+  float wk[U][K], wkn[U][K];
+  auto load = [&](int j0, unsigned (&di)[U][K], float (&dw)[U][K]) {
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = j0 + u * blockDim.x;
 #pragma unroll
       for (int k = 0; k < K; ++k) {
         // min(): memory safety only; valid indices are unchanged
-        id[u][k] = (j < J) ? min((unsigned)ib[(long long)k * J + j], pmax) : 0u;
-        wk[u][k] = (HAS_W && j < J) ? wb[(long long)k * J + j] : 1.f;
+        di[u][k] = (j < J) ? min((unsigned)ib[(long long)k * J + j], pmax) : 0u;
+        dw[u][k] = (HAS_W && j < J) ? wb[(long long)k * J + j] : 1.f;
       }
     }
+  };
+  // PIPE costs ~12 registers: only where one CTA owns the SM anyway (G == 1: big planes); the small-plane variants stay
+  // at 32 registers so that two CTAs of 1024 threads fit
+  constexpr bool PIPE = (G == 1);
+  if (PIPE) load(threadIdx.x, id, wk);
+  if (PLANE_SMEM) {
+    __syncthreads();  // mbarrier initialised (thread 0) and the tail loads done before anybody waits / reads
+    if (bulk > 0) mbar_wait(&bar, 0);
+  }
+  for (int j0 = threadIdx.x; j0 < J; j0 += blockDim.x * U) {
+    if (PIPE) load(j0 + blockDim.x * U, idn, wkn);  // out-of-range rounds load nothing (predicated)
+    else load(j0, id, wk);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int j = j0 + u * blockDim.x;
@@ -162,6 +183,15 @@ __global__ void __launch_bounds__(1024, 1)
         }
         ob[(long long)g * J + j] = acc;
       }
+    }
+    if (PIPE) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+#pragma unroll
+        for (int k = 0; k < K; ++k) {
+          id[u][k] = idn[u][k];
+          wk[u][k] = wkn[u][k];
+        }
     }
   }
 }
