@@ -16,6 +16,29 @@
 
 namespace pcfm {
 
+// A work item of the cell kernels and its header, fetched ONE ITEM AHEAD so that the header's L2 latency overlaps the
+// previous item's work: light slice -> x = cells entry, y = slot0 entry of this lane's cell; heavy piece -> the int4.
+struct CellItem {
+  int item;
+  int4 h;
+};
+__device__ __forceinline__ CellItem next_cell_item(int* counter, int nslice, int nitem, const int* __restrict__ cl,
+                                                   const int* __restrict__ sl, const int4* __restrict__ hv) {
+  const int lane = threadIdx.x & 31;
+  CellItem c;
+  c.item = 0;
+  if (lane == 0) c.item = atomicAdd(counter, 1);
+  c.item = __shfl_sync(0xffffffffu, c.item, 0);
+  c.h = make_int4(0, 0, 0, 0);
+  if (c.item < nslice) {
+    c.h.x = cl[(c.item << 5) | lane];
+    c.h.y = sl[(c.item << 5) | lane];
+  } else if (c.item < nitem) {
+    c.h = hv[c.item - nslice];
+  }
+  return c;
+}
+
 // -------------------------------------------------------------------------------------------------
 // avg_voxelize forward
 // -------------------------------------------------------------------------------------------------
@@ -68,34 +91,32 @@ __global__ void __launch_bounds__(1024, 2)
   const int nslice = meta[b * kMetaInts + 0] >> 5, nitem = nslice + meta[b * kMetaInts + 1];
   const int lane = threadIdx.x & 31;
   // work items taken by whole warps from a shared counter: slices of 32 light cells (longest first), then heavy cells
-  for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&next_item, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= nitem) break;
-    if (item < nslice) {
-      const int ci = (item << 5) | lane;
-      const int d = cl[ci];
+  const int4* hv = (const int4*)heavy + (long long)b * hcap;
+  CellItem cur = next_cell_item(&next_item, nslice, nitem, cl, sl, hv);
+  while (cur.item < nitem) {
+    const CellItem nxt = next_cell_item(&next_item, nslice, nitem, cl, sl, hv);  // header in flight during this item
+    if (cur.item < nslice) {
+      const int d = cur.h.x;
       const int n = (int)((unsigned)d >> 24), t = d & 0xffffff;
-      if (n == 0) continue;  // alignment hole (no warp-level operation below)
-      const int s0 = sl[ci] & 0xffffff;
-      const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
-      float acc = 0.f;
-      for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread, branch-free tail:
-        int p[4];                          // a padded slot re-reads the last record and contributes an exact +0
+      if (n != 0) {  // 0 = alignment hole
+        const int s0 = cur.h.y & 0xffffff;
+        const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
+        float acc = 0.f;
+        for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread, branch-free tail:
+          int p[4];                          // a padded slot re-reads the last record and contributes an exact +0
 #pragma unroll
-        for (int k = 0; k < 4; ++k) p[k] = rc[s0 + 32 * min(i0 + k, n - 1)];
+          for (int k = 0; k < 4; ++k) p[k] = rc[s0 + 32 * min(i0 + k, n - 1)];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
-          f = (i0 + k < n) ? f : 0.f;
-          acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
+          for (int k = 0; k < 4; ++k) {
+            float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
+            f = (i0 + k < n) ? f : 0.f;
+            acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
+          }
         }
+        o[t] = acc;
       }
-      o[t] = acc;
     } else {
-      const int4 hd = ((const int4*)heavy)[(long long)b * hcap + (item - nslice)];
-      const int t = hd.x, s0 = hd.y, n = hd.z;
+      const int t = cur.h.x, s0 = cur.h.y, n = cur.h.z;
       const float rcp = __frcp_rn((float)n);
       float acc = 0.f;
       for (int i = lane; i < n; i += 32 * PCFM_HEAVY_U) {  // PCFM_HEAVY_U independent record loads in flight per lane
@@ -112,6 +133,7 @@ __global__ void __launch_bounds__(1024, 2)
       acc = warp_sum(acc);
       if (lane == 0) o[t] = acc;
     }
+    cur = nxt;
   }
 }
 
@@ -187,20 +209,18 @@ __global__ void __launch_bounds__(1024, 1)
   //   [0, nslice)           slices of 32 light cells, longest cells first (count-sorted plan)
   //   [nslice, nslice + h1) pieces (<= kHeavyChunk records) of heavy cells
   const int nslice = l1 >> 5, nitem = nslice + h1;
-  for (;;) {
-    int item = 0;
-    if (lane == 0) item = atomicAdd(&next_item, 1);
-    item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= nitem) break;
-    if (item < nslice) {
+  const int4* hv = (const int4*)heavy + (long long)b * hcap;
+  CellItem cur = next_cell_item(&next_item, nslice, nitem, cl, sl, hv);
+  while (cur.item < nitem) {
+    const CellItem nxt = next_cell_item(&next_item, nslice, nitem, cl, sl, hv);  // header in flight during this item
+    if (cur.item < nslice) {
       // Light cells (sliced-ELL): one thread per cell sums the 8 corner contributions of its points in registers,
       // then adds them into the plane.  Neighbouring cells share voxels, so the add is a shared-memory atomicAdd
       // (a CAS loop on sm_100a; collisions need two adjacent cells to finish in the same few cycles).
-      const int ci = (item << 5) | lane;
-      const int d = cl[ci];
+      const int d = cur.h.x;
       const int n = (int)((unsigned)d >> 24);  // 0 = alignment hole
       const int cell = d & 0xffffff;
-      const unsigned se = (unsigned)sl[ci];
+      const unsigned se = (unsigned)cur.h.y;
       const int s0 = se & 0xffffff;
       const unsigned mask = n ? se >> 24 : 0u;
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -241,7 +261,7 @@ __global__ void __launch_bounds__(1024, 1)
     } else {
       // Heavy cell piece: the whole warp; the 8 partial sums are reduced by recursive halving (9 shuffles instead
       // of 40): after the exchange lane l holds the total of corner (l >> 2) & 7.
-      const int4 hd = ((const int4*)heavy)[(long long)b * hcap + (item - nslice)];
+      const int4 hd = cur.h;
       const int cell = hd.x, s0 = hd.y, n = hd.z;
       float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
       for (int i = lane; i < n; i += 32 * PCFM_HEAVY_V) {  // PCFM_HEAVY_V independent record loads in flight per lane
@@ -282,6 +302,7 @@ __global__ void __launch_bounds__(1024, 1)
         if ((hd.w >> k) & 1) atomicAdd(plane + cell + (k >> 2) * r2 + ((k >> 1) & 1) * r + (k & 1), a1);
       }
     }
+    cur = nxt;
   }
   if (!PLANE_SMEM) return;
   __syncthreads();
