@@ -102,17 +102,28 @@ __global__ void __launch_bounds__(1024, 2)
         const int s0 = cur.h.y & 0xffffff;
         const float rcp = __frcp_rn((float)n);  // == (float)(1.0/(float)cnt), vox.cu:65
         float acc = 0.f;
-        for (int i0 = 0; i0 < n; i0 += 4) {  // four independent record loads in flight per thread, branch-free tail:
-          int p[4];                          // a padded slot re-reads the last record and contributes an exact +0
-#pragma unroll
-          for (int k = 0; k < 4; ++k) p[k] = rc[s0 + 32 * min(i0 + k, n - 1)];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            float f = ROW_SMEM ? smem[p[k]] : __ldg(row_g + p[k]);
-            f = (i0 + k < n) ? f : 0.f;
-            acc = __fadd_rn(acc, __fmul_rn(f, rcp));  // product rounded, then added: the reference's atomicAdd(f*div)
-          }
+        // records walked 4 / 2 / 1 at a time in ascending order (independent loads in flight, immediate offsets, no
+        // padded work); every product is rounded, then added: the reference's atomicAdd(f * div)
+        auto feat = [&](int p) { return ROW_SMEM ? smem[p] : __ldg(row_g + p); };
+        const int* rp = rc + s0;
+        int i0 = 0;
+        for (; i0 + 4 <= n; i0 += 4, rp += 128) {
+          const int p0 = rp[0], p1 = rp[32], p2 = rp[64], p3 = rp[96];
+          const float f0 = feat(p0), f1 = feat(p1), f2 = feat(p2), f3 = feat(p3);
+          acc = __fadd_rn(acc, __fmul_rn(f0, rcp));
+          acc = __fadd_rn(acc, __fmul_rn(f1, rcp));
+          acc = __fadd_rn(acc, __fmul_rn(f2, rcp));
+          acc = __fadd_rn(acc, __fmul_rn(f3, rcp));
         }
+        if (i0 + 2 <= n) {
+          const int p0 = rp[0], p1 = rp[32];
+          const float f0 = feat(p0), f1 = feat(p1);
+          acc = __fadd_rn(acc, __fmul_rn(f0, rcp));
+          acc = __fadd_rn(acc, __fmul_rn(f1, rcp));
+          i0 += 2;
+          rp += 64;
+        }
+        if (i0 < n) acc = __fadd_rn(acc, __fmul_rn(feat(rp[0]), rcp));
         o[t] = acc;
       }
     } else {

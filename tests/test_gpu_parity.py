@@ -188,8 +188,11 @@ def test_trilinear_devoxelize(be, oracle, ref, kw):
         assert_equal(host(inds), host(r_inds), "inds vs reference")
         assert_equal(host(wgts), host(r_wgts), "wgts vs reference")
         assert_close(host(outs), host(r_outs), "outs vs reference")
+        # the reference adds ~40 signed terms per voxel with global atomics in arrival order: its own run-to-run spread
+        # needs the same 1e-5 absolute term as the oracle comparison above (1 failure in 25 runs at 1e-6)
         assert_close(host(be.pvcnn.trilinear_devoxelize_backward(cu(gy), inds, wgts, res)),
-                     host(ref["pvcnn"].trilinear_devoxelize_backward(cu(gy), r_inds, r_wgts, res)), "grad vs reference")
+                     host(ref["pvcnn"].trilinear_devoxelize_backward(cu(gy), r_inds, r_wgts, res)), "grad vs reference",
+                     atol_frac=1e-5)
 
 
 def test_devox_backward_generic_is_deterministic(be):
@@ -279,12 +282,13 @@ def test_fps_ballquery_grouping_gather_3nn(be, oracle, ref, kw):
         assert_equal(host(fidx), host(R.furthest_point_sampling(cu(pts), m)), "fps vs reference")
         assert_equal(host(bq), host(R.ball_query(centers, cu(pts), cases.BALL["radius"], cases.BALL["u"])), "ball vs reference")
         assert_equal(host(grp), host(R.grouping_forward(cu(feat), bq)), "grouping vs reference")
-        assert_close(host(ggx), host(R.grouping_backward(cu(ggy), bq, n)), "grouping bwd vs reference")
+        assert_close(host(ggx), host(R.grouping_backward(cu(ggy), bq, n)), "grouping bwd vs reference", atol_frac=1e-5)
         r3, ri3, rw3 = R.three_nearest_neighbors_interpolate_forward(cu(pts), centers, cu(cfeat))
         assert_equal(host(i3), host(ri3), "3nn idx vs reference")
         assert_equal(host(w3), host(rw3), "3nn w vs reference")
         assert_close(host(o3), host(r3), "3nn out vs reference")
-        assert_close(host(g3), host(R.three_nearest_neighbors_interpolate_backward(cu(feat), ri3, rw3, m)), "3nn bwd vs reference")
+        assert_close(host(g3), host(R.three_nearest_neighbors_interpolate_backward(cu(feat), ri3, rw3, m)), "3nn bwd vs reference",
+                     atol_frac=1e-5)
 
 
 def test_ball_query_no_hit_rows_are_zero(be):
