@@ -272,11 +272,32 @@ __global__ void __cluster_dims__(kFpsCl, 1, 1) __launch_bounds__(1024, 1)
 // =================================================================================================
 constexpr int kNnTile = 2048;
 
+// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): each lane rounded exactly like the scalar instruction
+__device__ __forceinline__ unsigned long long nn_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long nn_sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void nn_sq3x2(unsigned long long dx, unsigned long long dy, unsigned long long dz, float& lo,
+                                         float& hi) {  // sq3(): FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.)
+  unsigned long long t;
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(t));
+}
+
+
 __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ points,
                                                        const float* __restrict__ centers, int n, int m,
                                                        float* __restrict__ weights, int* __restrict__ indices) {
   griddep_launch_dependents();  // the interpolation gather behind this kernel may start staging its planes
-  __shared__ float cx[kNnTile], cy[kNnTile], cz[kNnTile];
+  __shared__ __align__(16) float cx[kNnTile], cy[kNnTile], cz[kNnTile];
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = j < n;
@@ -301,20 +322,38 @@ __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__
     }
     __syncthreads();
     if (valid) {
-      for (int k = 0; k < len; ++k) {
-        const float d = sq3(ux - cx[k], uy - cy[k], uz - cz[k]);
+      // four centres per step: one LDS.128 per coordinate, distances as packed pairs (FADD2 / FMUL2 / FFMA2, lanes
+      // rounded like the scalar sq3); the exact ordered insertion runs only when one of the four beats the third best
+      auto insert = [&](float d, int k) {
         if (d < best2) {
-          best2 = d; i2 = base + k;
+          best2 = d; i2 = k;
           if (d < best1) {
             best2 = best1; i2 = i1;
-            best1 = d; i1 = base + k;
+            best1 = d; i1 = k;
             if (d < best0) {
               best1 = best0; i1 = i0;
-              best0 = d; i0 = base + k;
+              best0 = d; i0 = k;
             }
           }
         }
+      };
+      const unsigned long long uxp = nn_pack2(ux, ux), uyp = nn_pack2(uy, uy), uzp = nn_pack2(uz, uz);
+      int k = 0;
+      for (; k + 4 <= len; k += 4) {
+        const ulonglong2 qx = *reinterpret_cast<const ulonglong2*>(cx + k);  // (x0,x1) (x2,x3)
+        const ulonglong2 qy = *reinterpret_cast<const ulonglong2*>(cy + k);
+        const ulonglong2 qz = *reinterpret_cast<const ulonglong2*>(cz + k);
+        float d0, d1, d2, d3;
+        nn_sq3x2(nn_sub2(uxp, qx.x), nn_sub2(uyp, qy.x), nn_sub2(uzp, qz.x), d0, d1);
+        nn_sq3x2(nn_sub2(uxp, qx.y), nn_sub2(uyp, qy.y), nn_sub2(uzp, qz.y), d2, d3);
+        if (fminf(fminf(d0, d1), fminf(d2, d3)) < best2) {
+          insert(d0, base + k);
+          insert(d1, base + k + 1);
+          insert(d2, base + k + 2);
+          insert(d3, base + k + 3);
+        }
       }
+      for (; k < len; ++k) insert(sq3(ux - cx[k], uy - cy[k], uz - cz[k]), base + k);
     }
   }
   if (!valid) return;
