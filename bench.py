@@ -264,13 +264,13 @@ def run_ours(args):
     tot_bytes = sum(algorithmic_bytes(n_, c, r) * len(ts) / 3 for (n_, c, r), ts in per.items())
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of that op's main kernel, one launch, from the committed capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01b_ncu_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_ncu_traffic.json")))
         traffic = tj["dram_bytes_per_launch"].get(f"{top['op']},{top['C']},{top['r']}")
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "hbm", "kernel": f"{top['op']} C={top['C']} r={top['r']} (op = plan kernels + row kernel)",
                 "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": round(top["GBps"] / peak, 4),
-                "traffic": traffic, "traffic_source": "profiles/r01b_ncu_traffic.json (ncu --set full, same shapes)",
+                "traffic": traffic, "traffic_source": "profiles/r01c_ncu_traffic.json (ncu --set full, same shapes)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": top_bytes,
                 "step_aggregate": {"algorithmic_GB_per_step": round(tot_bytes / 1e9, 3),
                                    "achieved_GBps": round(tot_bytes / (ms_per_step * 1e-3) / 1e9 * 1.0, 1),
