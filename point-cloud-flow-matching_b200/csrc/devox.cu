@@ -210,7 +210,7 @@ static int launch_devox_t(const float* coords, const float* feat, float* outs, i
 static int devox_group(int b, int c, int r) {
   if (devox_fwd_smem(1, r) > kDevoxSmemLimit) return 0;
   int g = 8;
-  while (g > 1 && (c % g != 0 || devox_fwd_smem(g, r) > 100 * 1024 || (long long)(c / g) * b < 2LL * num_sms()))
+  while (g > 1 && (c % g != 0 || devox_fwd_smem(g, r) > 100 * 1024 || (long long)(c / g) * b * 2 < 3LL * num_sms()))
     g >>= 1;
   return g;
 }
