@@ -221,10 +221,6 @@ constexpr int kPlanUnroll = 4;
 constexpr int kNB = kLightCap + 4;  // [1..lm] cells with that many points, [kLightCap+1] heavy cells, [kLightCap+2] their points
 constexpr int kH = kLightCap + 1, kHP = kLightCap + 2;
 
-#ifndef PCFM_PLAN_AGG
-#define PCFM_PLAN_AGG 1
-#endif
-
 __device__ __forceinline__ int cell_owner(int v) { return (v >> 5) % kCl; }
 __device__ __forceinline__ int cell_local(int v) { return (((v >> 5) / kCl) << 5) | (v & 31); }
 
@@ -278,7 +274,6 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
       const int i = i0 + u * nt + tid;
       const bool valid = i < i_hi && key[u] >= 0 && key[u] < t;
       rk[u] = -1;
-#if PCFM_PLAN_AGG
       // lanes of a warp that hit the same cell share one DSMEM atomic (dense clouds: most of a warp at r = 8)
       const unsigned act = __ballot_sync(0xffffffffu, valid);
       if (valid) {
@@ -289,9 +284,6 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
           old = atomicAdd(cluster.map_shared_rank(tab, cell_owner(key[u])) + cell_local(key[u]), __popc(peers));
         rk[u] = __shfl_sync(peers, old, leader) + __popc(peers & ((1u << lane) - 1u));
       }
-#else
-      if (valid) rk[u] = atomicAdd(cluster.map_shared_rank(tab, cell_owner(key[u])) + cell_local(key[u]), 1);
-#endif
       if (i < i_hi) {
         if (!single) rank[base + i] = rk[u];
         if (!TRI) ind_out[base + i] = key[u];
