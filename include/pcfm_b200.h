@@ -41,6 +41,11 @@ const char* pcfm_build_info(void);
 /* Number of kernel launches issued by this library in the calling process since load (or last reset). */
 int64_t pcfm_launch_count(void);
 void pcfm_reset_launch_count(void);
+/* Identity of the CUDA-graph capture that `stream` is recording, 0 when it is not capturing
+ * (cudaStreamGetCaptureInfo).  Host-side caches (pcfm.nn.Voxelization's per-coords memo) key on it: a tensor computed
+ * outside a capture must not be reused inside one — the graph would replay without the kernels that produce it. */
+unsigned long long pcfm_stream_capture_id(pcfm_stream_t stream);
+
 /* Tuning knob: "variant" selects alternative kernel implementations for A/B measurement.
  * key: "devox_bwd" (generic inds/wgts entry: 0 = sorted-segment gather [default], 1 = global RED atomics),
  *      "vox_fwd"   (0 = cell plan [default], 1 = global RED atomics, 2 = generic sorted-segment gather),

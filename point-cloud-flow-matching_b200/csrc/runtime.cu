@@ -56,6 +56,16 @@ const char* pcfm_build_info(void) {
 int64_t pcfm_launch_count(void) { return pcfm::g_launches; }
 void pcfm_reset_launch_count(void) { pcfm::g_launches = 0; }
 
+unsigned long long pcfm_stream_capture_id(pcfm_stream_t stream) {
+  cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
+  unsigned long long id = 0;
+  if (cudaStreamGetCaptureInfo((cudaStream_t)stream, &status, &id) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return 0;
+  }
+  return status == cudaStreamCaptureStatusActive ? id : 0;
+}
+
 int pcfm_set_option(const char* key, int value) {
   if (!key) return PCFM_E_BADARG;
   if (!strcmp(key, "devox_bwd")) { pcfm::g_opt_devox_bwd = value; return 0; }

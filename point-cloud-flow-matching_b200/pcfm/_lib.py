@@ -41,6 +41,7 @@ SIGNATURES = {
     "pcfm_gather_features_forward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "pcfm_gather_features_backward_workspace": (_sz, [_i, _i, _i, _i]),
     "pcfm_gather_features_backward": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_stream_capture_id": (ctypes.c_ulonglong, [_p]),
     "pcfm_voxel_coords": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
     "pcfm_furthest_point_sampling_workspace": (_sz, [_i, _i, _i]),
     "pcfm_furthest_point_sampling": (_i, [_p, _i, _i, _i, _p, _p, _sz, _p]),
@@ -100,3 +101,8 @@ def set_option(key, value):
 
 def build_info():
     return lib.pcfm_build_info().decode()
+
+
+def stream_capture_id(stream_ptr):
+    """Identity of the CUDA-graph capture recording on the stream (0 = not capturing)."""
+    return int(lib.pcfm_stream_capture_id(stream_ptr))

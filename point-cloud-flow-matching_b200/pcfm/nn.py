@@ -8,6 +8,7 @@ import weakref
 import torch
 import torch.nn as nn
 
+from . import _lib
 from . import functional as F
 
 __all__ = ["Voxelization", "PVConv", "SharedMLP", "SE3d", "BallQuery", "PointNetAModule", "PointNetSAModule",
@@ -20,16 +21,23 @@ class _VoxelCoordCache(threading.local):
     The PVConv layers of one backbone pass the same `coords` tensor object through (pvconv.py:39 returns it
     unchanged), so every layer after the first repeats identical reductions and elementwise kernels.  An entry is
     valid only while it is the same tensor object with the same autograd version counter (any in-place write
-    bumps it); the tensor is held by weak reference.  Level 1: centred coords and max norm (shared by all
-    resolutions); level 2: (norm_coords, vox_coords) per (resolution, normalize, eps).
+    bumps it) under the same CUDA-graph capture (or outside any): a value computed before a capture must not be
+    reused inside it, the graph would replay without the kernels that produce it.  The tensor is held by weak
+    reference.  Level 1: centred coords and max norm (shared by all resolutions); level 2: (norm_coords,
+    vox_coords) per (resolution, normalize, eps).
     """
 
     def __init__(self):
-        self.ref, self.version, self.centred, self.maxnorm, self.by_cfg = None, -1, None, None, {}
+        self.ref, self.version, self.capture = None, -1, 0
+        self.centred, self.maxnorm, self.by_cfg = None, None, {}
 
     def entry(self, coords):
-        if self.ref is None or self.ref() is not coords or coords._version != self.version:
-            self.ref, self.version = weakref.ref(coords), coords._version
+        capture = 0
+        if coords.is_cuda:
+            capture = _lib.stream_capture_id(torch.cuda.current_stream(coords.device).cuda_stream)
+        if (self.ref is None or self.ref() is not coords or coords._version != self.version
+                or capture != self.capture):
+            self.ref, self.version, self.capture = weakref.ref(coords), coords._version, capture
             self.centred, self.maxnorm, self.by_cfg = None, None, {}
         return self
 

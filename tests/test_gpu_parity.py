@@ -713,6 +713,39 @@ def test_cuda_graph_capture_of_a_pvconv_primitive_chain(be):
     assert_close(host(out), 2.0 * host(eager), "graph replay on updated inputs", rtol=1e-6, atol_frac=1e-6)
 
 
+def test_cuda_graph_capture_of_a_pvconv_stack_in_eval_mode(be):
+    """a sampler step (PVConv blocks in eval mode: Voxelization, our kernels with programmatic dependent
+    launches, cuDNN Conv3d / BatchNorm between them) is captured once and replayed on new data in the same buffers."""
+    from pcfm.nn import PVConv, SharedMLP
+    torch.manual_seed(3)
+    net = torch.nn.ModuleList([PVConv(8, 16, 3, 8, with_se=True, normalize=True, eps=1e-6), SharedMLP(16, [16]),
+                               PVConv(16, 16, 3, 8, with_se=False, normalize=True, eps=1e-6)]).cuda().eval()
+
+    def run(f, c):
+        for layer in net:
+            f, c = layer((f, c))
+        return f
+
+    f = torch.randn(2, 8, 3000, device="cuda")
+    c = torch.randn(2, 3, 3000, device="cuda")
+    f2, c2 = torch.randn_like(f), torch.randn_like(c)
+    with torch.no_grad():
+        want = run(f2.clone(), c2.clone())
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                run(f, c)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = run(f, c)
+        f.copy_(f2); c.copy_(c2)     # new inputs in the captured buffers
+        g.replay()
+        torch.cuda.synchronize()
+    assert_close(host(out), host(want), "graph replay vs eager", rtol=1e-5, atol_frac=1e-5)
+
+
 # ------------------------------------------------------------------------------------------------ randomized shapes
 def test_random_small_shapes_pvconv_primitives(be, oracle):
     """40 random (B, C, N, r) combinations, odd sizes included: ragged tails, unaligned rows (no TMA), r not a power
