@@ -43,6 +43,9 @@ CONFIG = {
     "workload": "BASELINE.json configs[1]: PVConv primitive chain of one velocity-net step, B=8, N=20000, "
                 "(C,r) = 2x(128,32) 2x(256,16) 2x(256,8); vox fwd + devox fwd(train) + devox bwd + vox bwd per instance",
     "batch": B, "points": NPTS, "stages": STAGES,
+    "plans": "the two PVConv blocks of a stage share one coords tensor (models.py:385-389), so the second block's "
+             "avg_voxelize forward / devoxelize backward reuse the first block's cell plan (pcfm_*_planned); the plan "
+             "memo is cleared at the start of EVERY step (new point clouds every training step): 6 plan builds per step",
     "l2": "inputs larger than L2: ~4.8 GB touched per step, every primitive reads tensors not written in that step",
     "parallelism": "one process per GPU, replicas (data parallel), no data-path collective",
 }
@@ -60,45 +63,78 @@ def algorithmic_bytes(op, c, r, b=B, n=NPTS):
 
 # --------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms from the last warm-up steps to the end of the timed
-    region (the timed region alone is ~0.1 s)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the warm-up tail and the timed region: an NVML thread (10 ms
+    period; `nvidia-smi -lms` needs ~0.5 s to produce its first line and the timed region is ~0.1 s), `nvidia-smi`
+    one-shot as the fall-back when pynvml cannot initialise."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        import threading
+        self.gpu_index = gpu_index
+        self.sm, self.bits, self.mx, self.src = [], 0, None, None
+        self._stop = threading.Event()
+        self._t = None
         try:
-            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
-                                      stderr=subprocess.DEVNULL)
-        except OSError:
-            self.p = None
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = gpu_index
+            if vis:
+                ids = [v.strip() for v in vis.split(",") if v.strip()]
+                if gpu_index < len(ids) and ids[gpu_index].isdigit():
+                    phys = int(ids[gpu_index])
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.src = "nvml"
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        except Exception:  # noqa: BLE001
+            self.nv = None
+
+    def _reasons(self):
+        for fn in ("nvmlDeviceGetCurrentClocksEventReasons", "nvmlDeviceGetCurrentClocksThrottleReasons"):
+            f = getattr(self.nv, fn, None)
+            if f is not None:
+                try:
+                    return int(f(self.h))
+                except Exception:  # noqa: BLE001
+                    continue
+        return 0
+
+    def _loop(self):
+        while not self._stop.is_set():
+            try:
+                self.sm.append(float(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM)))
+                self.bits |= self._reasons()
+            except Exception:  # noqa: BLE001
+                pass
+            self._stop.wait(0.01)
+
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            o = subprocess.run(["nvidia-smi", "-i", str(self.gpu_index), f"--query-gpu={q}",
+                                "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=20).stdout
+            r = [c.strip() for c in o.strip().splitlines()[0].split(",")]
+            self.sm.append(float(r[0])); self.mx = float(r[1]); self.src = "nvidia-smi (one sample, end of timed region)"
+            for (name, bit), v in zip(self.REASONS, r[2:6]):
+                if v.lower().startswith("active"):
+                    self.bits |= bit
+        except Exception:  # noqa: BLE001
+            pass
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
-            return out
-        self.p.terminate()
-        try:
-            self.p.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.p.kill()
-        self.f.flush()
-        rows = [[c.strip() for c in ln.strip().split(",")] for ln in open(self.f.name) if ln.strip()]
-        os.unlink(self.f.name)
-        sm, mx, reasons = [], [], set()
-        for r in rows:
-            try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
-            except (ValueError, IndexError):
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[3:7]):
-                if v.strip().lower().startswith("active"):
-                    reasons.add(name)
-        if sm:
-            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
-                   "samples": len(sm)}
-        return out
+        if self._t is not None:
+            self._stop.set()
+            self._t.join(timeout=2)
+        if not self.sm:
+            self._smi_once()
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "source": "unavailable"}
+        return {"sm_mhz": statistics.median(self.sm), "sm_min_mhz": min(self.sm), "sm_max_mhz": self.mx,
+                "reasons": sorted(n for n, b in self.REASONS if self.bits & b), "samples": len(self.sm),
+                "source": self.src}
 
 
 def measured_peak_gbs():
@@ -193,13 +229,16 @@ def run_ours(args):
     # ---------------- resident inputs: distinct buffers per PVConv instance ----------------
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     chains = []
-    for (c, r) in STAGES:
+    for k, (c, r) in enumerate(STAGES):
         feat = torch.randn(B, c, NPTS, device=dev, generator=g)
-        coords = torch.randn(B, 3, NPTS, device=dev, generator=g)
-        nc = coords - coords.mean(2, keepdim=True)                         # modules/voxelization.py:16-24
-        nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 1e-6) + 0.5
-        nc = torch.clamp(nc * r, 0, r - 1).contiguous()
-        vox = torch.round(nc).to(torch.int32).contiguous()
+        if k % 2 == 1 and STAGES[k - 1] == (c, r):      # second block of a stage: the SAME coords tensor objects
+            nc, vox = chains[-1]["nc"], chains[-1]["vox"]
+        else:
+            coords = torch.randn(B, 3, NPTS, device=dev, generator=g)
+            nc = coords - coords.mean(2, keepdim=True)                         # modules/voxelization.py:16-24
+            nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 1e-6) + 0.5
+            nc = torch.clamp(nc * r, 0, r - 1).contiguous()
+            vox = torch.round(nc).to(torch.int32).contiguous()
         chains.append(dict(c=c, r=r, feat=feat, nc=nc, vox=vox,
                            conv_out=torch.randn(B, c, r ** 3, device=dev, generator=g),     # what devox fwd reads
                            gy=torch.randn(B, c, NPTS, device=dev, generator=g),             # upstream grad of devox
@@ -207,6 +246,7 @@ def run_ours(args):
     P = be.pvcnn
 
     def step(rec=None):
+        be.plan_memo.clear()        # a training step sees new clouds: no plan survives from the previous step
         for ch in chains:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if rec is not None else None
             if ev: ev[0].record()
@@ -268,7 +308,8 @@ def run_ours(args):
         traffic = tj["dram_bytes_per_launch"].get(f"{top['op']},{top['C']},{top['r']}")
     except Exception:  # noqa: BLE001
         pass
-    roofline = {"bound": "hbm", "kernel": f"{top['op']} C={top['C']} r={top['r']} (op = plan kernels + row kernel)",
+    roofline = {"bound": "hbm", "kernel": f"{top['op']} C={top['C']} r={top['r']} (op = row kernel + its share of the stage's plan build: "
+                          "mean over the two blocks of the stage)",
                 "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": round(top["GBps"] / peak, 4),
                 "traffic": traffic, "traffic_source": "profiles/r01c_ncu_traffic.json (ncu --set full, same shapes)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": top_bytes,

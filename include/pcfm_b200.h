@@ -113,6 +113,20 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
                                               float* grad_x, void* workspace, size_t workspace_bytes,
                                               pcfm_stream_t stream);
 
+/* Plan reuse.  pcfm_avg_voxelize_forward and pcfm_trilinear_devoxelize_backward_coords group the points by voxel
+ * cell first (the "cell plan", a pure function of coords, b, n, r) and leave that plan in the caller's workspace.  The
+ * PVConv blocks of one stage of the reference's ContextNet see the SAME coordinates (models.py:385-389 passes them
+ * through, pvconv.py:39 returns them unchanged), so the second block - and the second backward - can skip the build:
+ * the two entries below take the workspace of an earlier call with identical (coords, b, n, r), untouched since, and
+ * launch only the row kernel.  Results are those of the unplanned entries on the same coords.  The caller owns the
+ * validity of the plan (pcfm/backend.py keys its memo on tensor identity + version + CUDA-graph capture + stream). */
+int pcfm_avg_voxelize_forward_planned(const float* features, int b, int c, int n, int r, float* out,
+                                      const void* plan_workspace, size_t plan_workspace_bytes,
+                                      pcfm_stream_t stream);
+int pcfm_trilinear_devoxelize_backward_planned(const float* grad_y, int b, int c, int n, int r, float* grad_x,
+                                               const void* plan_workspace, size_t plan_workspace_bytes,
+                                               pcfm_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Ball query / grouping / gather / FPS / 3-NN  (src/ball_query, src/grouping, src/sampling,
  *                                               src/interpolate/neighbor_interpolate.*)

@@ -48,10 +48,13 @@ __global__ void __launch_bounds__(1024, 2)
                         const int* __restrict__ slot0, const int* __restrict__ meta,
                         const int* __restrict__ heavy,
                         const int* __restrict__ rec, float* __restrict__ out, int C, int N, int T, int lcap,
-                        int hcap, int rcap, int use_tma) {
+                        int hcap, int rcap, int use_tma, int wait_first) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
   __shared__ int next_item;
+  // plan reused from an earlier call: the predecessor on the stream is an arbitrary kernel (it may produce `feat` or
+  // still read the memory `out` now occupies), so nothing global is touched before it has completed
+  if (wait_first) griddep_wait();
   const int c = blockIdx.x, b = blockIdx.y;
   const float* row_g = feat + ((long long)b * C + c) * N;
   float* o = out + ((long long)b * C + c) * T;
@@ -175,10 +178,11 @@ __global__ void __launch_bounds__(1024, 1)
                           const int* __restrict__ slot0, const int* __restrict__ meta,
                           const int* __restrict__ heavy, const float4* __restrict__ rec,
                           float* __restrict__ grad_x, int C, int N, int r, int lcap, int hcap, int rcap,
-                          int use_tma) {
+                          int use_tma, int wait_first) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
   __shared__ int next_item;
+  if (wait_first) griddep_wait();  // reused plan: see vox_fwd_cell_kernel
   const int r2 = r * r, P = r2 * r;
   const int c = blockIdx.x, b = blockIdx.y;
   const float* row_g = grad_y + ((long long)b * C + c) * N;
@@ -343,6 +347,67 @@ int avg_voxelize_forward_generic(const float* features, const int* coords, int b
                                  int* ind, int* cnt, void* workspace, size_t workspace_bytes, cudaStream_t st,
                                  int variant);
 
+static int launch_vox_fwd(const float* features, const CellPlan& plan, int b, int c, int n, int t, float* out,
+                          cudaStream_t st, bool reused) {
+  dim3 grid(c, b);
+  // fresh plan: programmatic dependent of the plan kernel; reused plan: chained PDL behind whatever ran before
+  const bool dep = reused ? g_opt_pdl >= 2 : plan.pdl;
+  PCFM_CUDA(allow_dyn_smem((const void*)vox_fwd_cell_kernel<true>, (int)(kMaxStageFloats * sizeof(float))));
+  if (n <= kMaxStageFloats)
+    PCFM_CUDA(launch_dependent(vox_fwd_cell_kernel<true>, grid, dim3(1024), (size_t)n * sizeof(float), st, dep,
+                               features, plan.cells, plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c,
+                               n, t, plan.lcap, plan.hcap, plan.rcap, (int)(g_opt_stage == 0), (int)reused));
+  else
+    PCFM_CUDA(launch_dependent(vox_fwd_cell_kernel<false>, grid, dim3(1024), 0, st, dep, features, plan.cells,
+                               plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c, n, t, plan.lcap,
+                               plan.hcap, plan.rcap, 0, (int)reused));
+  PCFM_LAUNCHED();
+  return 0;
+}
+
+// coords != nullptr: build the trilinear plan into `workspace`, else attach to the one an earlier call left there
+static int devox_bwd_cells(const float* grad_y, const float* coords, int b, int c, int n, int r, float* grad_x,
+                           void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  const int t = r * r * r;
+  const bool reused = coords == nullptr;
+  const bool plane_smem = devox_bwd_smem(0, r, false) <= kSmemLimit;  // r <= 37
+  if (n == 0 || !plane_smem) {
+    PCFM_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)b * c * t * sizeof(float), st));
+    if (n == 0) return 0;
+  }
+  Workspace ws(workspace, workspace_bytes);
+  CellPlan plan;
+  int rc = reused ? cellplan_attach(true, b, n, t, &plan, &ws)
+                  : cellplan_build(nullptr, coords, r, nullptr, b, n, t, nullptr, &plan, &ws, st);
+  if (rc) return rc;
+  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kSmemLimit));
+  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kSmemLimit));
+  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kSmemLimit));
+  dim3 grid(c, b);
+  const bool row_smem = devox_bwd_smem(n, r, true, plane_smem) <= kSmemLimit;
+  const size_t smem = devox_bwd_smem(n, r, row_smem, plane_smem);
+  // small footprints (r <= 16, or no plane): two CTAs of 512 threads per SM overlap one CTA's staging with the
+  // other's compute
+  const int threads = (row_smem && smem <= 110 * 1024) ? 512 : 1024;
+  const int tma = (int)(g_opt_stage == 0);
+  // a reused plan behind a memset must not start early (the kernel adds to the zeroed grid with global atomics)
+  const bool dep = reused ? (g_opt_pdl >= 2 && plane_smem) : plan.pdl;
+#define PCFM_DBWD(RS, PS)                                                                                         \
+  PCFM_CUDA(launch_dependent(devox_bwd_cell_kernel<RS, PS>, grid, dim3(threads), smem, st, dep, grad_y,            \
+                             plan.cells, plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec, grad_x, c, n, \
+                             r, plan.lcap, plan.hcap, plan.rcap, tma, (int)reused))
+  if (plane_smem && row_smem) PCFM_DBWD(true, true);
+  else if (plane_smem) PCFM_DBWD(false, true);
+  else if (row_smem) PCFM_DBWD(true, false);
+  else PCFM_DBWD(false, false);
+#undef PCFM_DBWD
+  PCFM_LAUNCHED();
+  return 0;
+}
+
 }  // namespace pcfm
 
 using namespace pcfm;
@@ -373,18 +438,21 @@ int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, i
   CellPlan plan;
   int rc = cellplan_build(coords, nullptr, r, ind, b, n, t, cnt, &plan, &ws, st);
   if (rc || c == 0) return rc;
-  dim3 grid(c, b);
-  PCFM_CUDA(allow_dyn_smem((const void*)vox_fwd_cell_kernel<true>, (int)(kMaxStageFloats * sizeof(float))));
-  if (n <= kMaxStageFloats)
-    PCFM_CUDA(launch_dependent(vox_fwd_cell_kernel<true>, grid, dim3(1024), (size_t)n * sizeof(float), st, plan.pdl,
-                               features, plan.cells, plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c,
-                               n, t, plan.lcap, plan.hcap, plan.rcap, (int)(g_opt_stage == 0)));
-  else
-    PCFM_CUDA(launch_dependent(vox_fwd_cell_kernel<false>, grid, dim3(1024), 0, st, plan.pdl, features, plan.cells,
-                               plan.slot0, plan.meta, plan.heavy, (const int*)plan.rec, out, c, n, t, plan.lcap,
-                               plan.hcap, plan.rcap, 0));
-  PCFM_LAUNCHED();
-  return 0;
+  return launch_vox_fwd(features, plan, b, c, n, t, out, st, false);
+}
+
+int pcfm_avg_voxelize_forward_planned(const float* features, int b, int c, int n, int r, float* out,
+                                      const void* plan_workspace, size_t plan_workspace_bytes,
+                                      pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || r <= 0 || (long long)r * r * r > (1 << 24)) return PCFM_E_BADARG;
+  if (b == 0 || c == 0) return 0;
+  if (!out || !plan_workspace || (n > 0 && !features)) return PCFM_E_BADARG;
+  const int t = r * r * r;
+  Workspace ws(const_cast<void*>(plan_workspace), plan_workspace_bytes);
+  CellPlan plan;
+  int rc = cellplan_attach(false, b, n, t, &plan, &ws);
+  if (rc) return rc;
+  return launch_vox_fwd(features, plan, b, c, n, t, out, (cudaStream_t)stream, true);
 }
 
 size_t pcfm_trilinear_devoxelize_backward_coords_workspace(int b, int c, int n, int r) {
@@ -399,43 +467,19 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
   if (b < 0 || c < 0 || n < 0 || r <= 0) return PCFM_E_BADARG;
   if (b == 0 || c == 0) return 0;
   if (!grad_x || (n > 0 && (!grad_y || !coords))) return PCFM_E_BADARG;
-  cudaStream_t st = (cudaStream_t)stream;
-  const long long tl = (long long)r * r * r;
-  if (tl > (1 << 24)) return PCFM_E_BADARG;  // 24-bit cell ids in the plan (r <= 256)
-  const int t = (int)tl;
-  const bool plane_smem = devox_bwd_smem(0, r, false) <= kSmemLimit;  // r <= 37
-  if (n == 0 || !plane_smem) {
-    PCFM_CUDA(cudaMemsetAsync(grad_x, 0, (size_t)b * c * t * sizeof(float), st));
-    if (n == 0) return 0;
-  }
-  Workspace ws(workspace, workspace_bytes);
-  CellPlan plan;
-  int rc = cellplan_build(nullptr, coords, r, nullptr, b, n, t, nullptr, &plan, &ws, st);
-  if (rc) return rc;
-  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kSmemLimit));
-  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kSmemLimit));
-  PCFM_CUDA(cudaFuncSetAttribute(devox_bwd_cell_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kSmemLimit));
-  dim3 grid(c, b);
-  const bool row_smem = devox_bwd_smem(n, r, true, plane_smem) <= kSmemLimit;
-  const size_t smem = devox_bwd_smem(n, r, row_smem, plane_smem);
-  // small footprints (r <= 16, or no plane): two CTAs of 512 threads per SM overlap one CTA's staging with the
-  // other's compute
-  const int threads = (row_smem && smem <= 110 * 1024) ? 512 : 1024;
-  const int tma = (int)(g_opt_stage == 0);
-#define PCFM_DBWD(RS, PS)                                                                                         \
-  PCFM_CUDA(launch_dependent(devox_bwd_cell_kernel<RS, PS>, grid, dim3(threads), smem, st, plan.pdl, grad_y,       \
-                             plan.cells, plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec, grad_x, c, n, \
-                             r, plan.lcap, plan.hcap, plan.rcap, tma))
-  if (plane_smem && row_smem) PCFM_DBWD(true, true);
-  else if (plane_smem) PCFM_DBWD(false, true);
-  else if (row_smem) PCFM_DBWD(true, false);
-  else PCFM_DBWD(false, false);
-#undef PCFM_DBWD
-  PCFM_LAUNCHED();
-  return 0;
+  if ((long long)r * r * r > (1 << 24)) return PCFM_E_BADARG;  // 24-bit cell ids in the plan (r <= 256)
+  return devox_bwd_cells(grad_y, coords, b, c, n, r, grad_x, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int pcfm_trilinear_devoxelize_backward_planned(const float* grad_y, int b, int c, int n, int r, float* grad_x,
+                                               const void* plan_workspace, size_t plan_workspace_bytes,
+                                               pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || r <= 0) return PCFM_E_BADARG;
+  if (b == 0 || c == 0) return 0;
+  if (!grad_x || !plan_workspace || (n > 0 && !grad_y)) return PCFM_E_BADARG;
+  if ((long long)r * r * r > (1 << 24)) return PCFM_E_BADARG;
+  return devox_bwd_cells(grad_y, nullptr, b, c, n, r, grad_x, const_cast<void*>(plan_workspace),
+                         plan_workspace_bytes, (cudaStream_t)stream);
 }
 
 }  // extern "C"

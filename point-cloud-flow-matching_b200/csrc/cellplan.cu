@@ -420,26 +420,48 @@ size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear)
   return s + 256;
 }
 
-int cellplan_build(const int* vox_coords, const float* float_coords, int r, int* ind_out, int b, int n, int t,
-                   int* cnt, CellPlan* plan, Workspace* ws, cudaStream_t st) {
-  const bool tri = float_coords != nullptr;
+// Carves the plan arrays (and the build scratch) out of the workspace.  The carve is a pure function of
+// (trilinear, b, n, t), so a workspace left behind by cellplan_build() can be re-attached later (cellplan_attach).
+struct PlanScratch {
+  int *zero_block, *ctr, *rank, *aux, *recbase;
+  size_t zero_ints;
+};
+static bool cellplan_carve(bool tri, int b, int n, int t, CellPlan* plan, Workspace* ws, PlanScratch* sc) {
   plan->lcap = (int)lcap_of(n, t);
   plan->light_max = tri ? kLightMaxTri : kLightMaxMean;
   plan->chunk = tri ? kHeavyChunk : 0x7fffffff;  // mean plans: the consumer stores a cell's mean, no pieces
   plan->hcap = n / (plan->light_max + 1) + (tri ? n / kHeavyChunk : 0) + 2;
   plan->rcap = n + kEllPad;
   // cells and the counters are zeroed by ONE memset: they are carved from one block
-  const size_t zero_ints = (size_t)b * plan->lcap + (size_t)b * kCtr;
-  int* zero_block = ws->take<int>(zero_ints);
-  plan->cells = zero_block;
-  int* ctr = zero_block ? zero_block + (size_t)b * plan->lcap : nullptr;
+  sc->zero_ints = (size_t)b * plan->lcap + (size_t)b * kCtr;
+  sc->zero_block = ws->take<int>(sc->zero_ints);
+  plan->cells = sc->zero_block;
+  sc->ctr = sc->zero_block ? sc->zero_block + (size_t)b * plan->lcap : nullptr;
   plan->slot0 = ws->take<int>((size_t)b * plan->lcap);
   plan->meta = ws->take<int>((size_t)b * kMetaInts);
   plan->heavy = (int*)ws->take<int4>((size_t)b * plan->hcap);
   plan->rec = tri ? (void*)ws->take<float4>((size_t)b * plan->rcap) : (void*)ws->take<int>((size_t)b * plan->rcap);
-  int* rank = ws->take<int>((size_t)b * n);
-  int* aux = ws->take<int>((size_t)b * t);
-  int* recbase = ws->take<int>((size_t)b * t);
+  sc->rank = ws->take<int>((size_t)b * n);
+  sc->aux = ws->take<int>((size_t)b * t);
+  sc->recbase = ws->take<int>((size_t)b * t);
+  return ws->ok();
+}
+
+int cellplan_attach(bool tri, int b, int n, int t, CellPlan* plan, Workspace* ws) {
+  PlanScratch sc;
+  if (!cellplan_carve(tri, b, n, t, plan, ws, &sc)) return PCFM_E_WORKSPACE;
+  plan->pdl = false;  // no plan kernel in front of the consumer
+  return 0;
+}
+
+int cellplan_build(const int* vox_coords, const float* float_coords, int r, int* ind_out, int b, int n, int t,
+                   int* cnt, CellPlan* plan, Workspace* ws, cudaStream_t st) {
+  const bool tri = float_coords != nullptr;
+  PlanScratch sc;
+  cellplan_carve(tri, b, n, t, plan, ws, &sc);
+  int* zero_block = sc.zero_block;
+  int *ctr = sc.ctr, *rank = sc.rank, *aux = sc.aux, *recbase = sc.recbase;
+  const size_t zero_ints = sc.zero_ints;
   if (!cnt) cnt = ws->take<int>((size_t)b * t);
   if (!ws->ok()) return PCFM_E_WORKSPACE;
   const int tq = (cdiv(cdiv(t, 32), kCl)) * 32;  // cells per CTA of the cluster

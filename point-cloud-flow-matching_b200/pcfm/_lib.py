@@ -34,6 +34,8 @@ SIGNATURES = {
     "pcfm_trilinear_devoxelize_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_trilinear_devoxelize_backward_coords_workspace": (_sz, [_i, _i, _i, _i]),
     "pcfm_trilinear_devoxelize_backward_coords": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_avg_voxelize_forward_planned": (_i, [_p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_trilinear_devoxelize_backward_planned": (_i, [_p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_ball_query": (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _p]),
     "pcfm_grouping_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pcfm_grouping_backward_workspace": (_sz, [_i, _i, _i, _i, _i]),
@@ -95,8 +97,15 @@ def reset_launch_count():
     lib.pcfm_reset_launch_count()
 
 
+options = {}           # what set_option() was last called with
+option_listeners = []  # callables run after every set_option (backend.plan_memo drops its plans)
+
+
 def set_option(key, value):
     check(lib.pcfm_set_option(key.encode(), int(value)), f"pcfm_set_option({key})")
+    options[key] = int(value)
+    for fn in option_listeners:
+        fn()
 
 
 def build_info():

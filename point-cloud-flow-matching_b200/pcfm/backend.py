@@ -8,6 +8,9 @@ Same function names, argument order, return structure and error behaviour (argum
 RuntimeError exactly where the reference's TORCH_CHECKs do, utils.hpp:7-18).  torch is used for device
 memory and the current stream only; all arithmetic happens in libpcfm_b200.so.
 """
+import threading
+import weakref
+
 import torch
 
 from . import _lib
@@ -52,6 +55,61 @@ def _chk(x, name, kind):
     (_check_float if kind == "f" else _check_int)(x, name)
 
 
+class _PlanMemo(threading.local):
+    """Per-thread memo of cell plans (include/pcfm_b200.h, "Plan reuse"), keyed on the coordinate tensor.
+
+    The PVConv blocks of one ContextNet stage voxelize / devoxelize at the SAME coords tensor and resolution
+    (models.py:385-389; pcfm.nn.Voxelization hands every block of a stage the same (norm_coords, vox_coords) tensor
+    objects), so the plan built by the first avg_voxelize_forward serves the second, and the plan built by the first
+    trilinear_devoxelize_backward_coords of the backward pass serves the second.  An entry is valid only for the same
+    tensor OBJECT (held by weak reference, so a recycled address cannot alias) with the same autograd version
+    counter, shape, resolution, stream and CUDA-graph capture.  `plan_memo.enabled = False` switches it off;
+    `plan_memo.clear()` drops every plan (a write through `.data` or a raw pointer bypasses the version counter).
+    """
+
+    CAPACITY = 8  # 3 stages x (mean, trilinear) per step and some slack; ~6 MB per entry at B=8, N=20000
+
+    def __init__(self):
+        self.enabled = True
+        self.entries = {}  # key -> (weakref(coords), version, payload); insertion order = age
+        self.hits = self.misses = 0
+
+    @staticmethod
+    def _key(kind, coords, r):
+        st = torch.cuda.current_stream(coords.device)
+        return (kind, id(coords), tuple(coords.shape), int(r), coords.device.index, st.cuda_stream,
+                _lib.stream_capture_id(st.cuda_stream))
+
+    def get(self, kind, coords, r):
+        if not self.enabled:
+            return None
+        key = self._key(kind, coords, r)
+        e = self.entries.get(key)
+        if e is not None and e[0]() is coords and e[1] == coords._version:
+            self.hits += 1
+            return e[2]
+        if e is not None:
+            del self.entries[key]
+        self.misses += 1
+        return None
+
+    def put(self, kind, coords, r, payload):
+        if not self.enabled:
+            return
+        for k in [k for k, e in self.entries.items() if e[0]() is None]:  # coords tensor died
+            del self.entries[k]
+        while len(self.entries) >= self.CAPACITY:
+            del self.entries[next(iter(self.entries))]
+        self.entries[self._key(kind, coords, r)] = (weakref.ref(coords), coords._version, payload)
+
+    def clear(self):
+        self.entries.clear()
+
+
+plan_memo = _PlanMemo()
+_lib.option_listeners.append(plan_memo.clear)  # an A/B option may change what a workspace holds
+
+
 class _PvcnnBackend:
     """`_pvcnn_backend` (bindings.cpp:10-37)."""
 
@@ -65,14 +123,23 @@ class _PvcnnBackend:
         s = r * r * r
         dev = features.device
         out = torch.empty((b, c, s), dtype=torch.float32, device=dev)
-        ind = torch.empty((b, n), dtype=torch.int32, device=dev)
-        cnt = torch.empty((b, s), dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
+            hit = plan_memo.get("mean", coords, r) if n > 0 and c > 0 else None
+            if hit is not None:  # same coords tensor as an earlier call: reuse its cell plan, ind and cnt
+                ws, ind, cnt = hit
+                check(lib.pcfm_avg_voxelize_forward_planned(_ptr(features), b, c, n, r, _ptr(out), _ptr(ws),
+                                                            ws.numel(), _stream(features)),
+                      "avg_voxelize_forward_planned")
+                return [out, ind, cnt]
+            ind = torch.empty((b, n), dtype=torch.int32, device=dev)
+            cnt = torch.empty((b, s), dtype=torch.int32, device=dev)
             nb = lib.pcfm_avg_voxelize_forward_workspace(b, c, n, r)
             ws = _ws(nb, dev)
             check(lib.pcfm_avg_voxelize_forward(_ptr(features), _ptr(coords), b, c, n, r, _ptr(out), _ptr(ind),
                                                 _ptr(cnt), _ptr(ws), ws.numel(), _stream(features)),
                   "avg_voxelize_forward")
+            if n > 0 and c > 0 and _lib.options.get("vox_fwd", 0) == 0:  # generic variants leave no cell plan
+                plan_memo.put("mean", coords, r, (ws, ind, cnt))
         return [out, ind, cnt]
 
     @staticmethod
@@ -162,10 +229,18 @@ class _PvcnnBackend:
         dev = grad_y.device
         grad_x = torch.empty((b, c, r * r * r), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            ws = plan_memo.get("tri", coords, r) if n > 0 and c > 0 else None
+            if ws is not None:
+                check(lib.pcfm_trilinear_devoxelize_backward_planned(_ptr(grad_y), b, c, n, r, _ptr(grad_x), _ptr(ws),
+                                                                     ws.numel(), _stream(grad_y)),
+                      "trilinear_devoxelize_backward_planned")
+                return grad_x
             ws = _ws(lib.pcfm_trilinear_devoxelize_backward_coords_workspace(b, c, n, r), dev)
             check(lib.pcfm_trilinear_devoxelize_backward_coords(_ptr(grad_y), _ptr(coords), b, c, n, r, _ptr(grad_x),
                                                                 _ptr(ws), ws.numel(), _stream(grad_y)),
                   "trilinear_devoxelize_backward_coords")
+            if n > 0 and c > 0:
+                plan_memo.put("tri", coords, r, ws)
         return grad_x
 
     # ---- ball query (ball_query.cpp:6-30) ----

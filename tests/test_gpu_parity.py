@@ -586,7 +586,7 @@ def test_voxelization_coordinate_memo(be):
     _, nc_a = v16(f, c)
     n0 = _lib.launch_count()
     _, nc_b = v16b(f, c)                    # other instance, same configuration: memo hit
-    assert nc_b is nc_a and _lib.launch_count() - n0 == 2      # cell plan + voxelize kernel only
+    assert nc_b is nc_a and _lib.launch_count() - n0 == 1      # voxelize kernel only: coords AND cell plan memoised
     _, nc_8 = v8(f, c)                      # other resolution: shares the centred coords / max norm
     assert torch.equal(nc_8, _torch_voxel_coords(c, 8, True, 1e-6)[0])
     c.mul_(0.5)                             # in-place write bumps the version counter
@@ -744,6 +744,116 @@ def test_cuda_graph_capture_of_a_pvconv_stack_in_eval_mode(be):
         g.replay()
         torch.cuda.synchronize()
     assert_close(host(out), host(want), "graph replay vs eager", rtol=1e-5, atol_frac=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ plan reuse
+PLAN_SHAPES = [dict(seed=301, b=2, c=8, n=20000, res=32), dict(seed=302, b=3, c=12, n=5000, res=16),
+               dict(seed=303, b=2, c=6, n=20000, res=8), dict(seed=304, b=1, c=5, n=777, res=5),
+               dict(seed=305, b=1, c=3, n=3000, res=40)]   # r=40: no shared-memory plane (global atomics on a memset)
+
+
+@pytest.mark.parametrize("kw", PLAN_SHAPES, ids=lambda k: f"b{k['b']}c{k['c']}n{k['n']}r{k['res']}")
+def test_plan_reuse_matches_fresh_build(be, oracle, kw):
+    """include/pcfm_b200.h "Plan reuse": the second PVConv block of a stage sees the same coords tensor; its
+    avg_voxelize forward / devoxelize backward run on the plan the first block's call left behind
+    (pcfm_*_planned).  Same results as a fresh build, checked against the oracle as well."""
+    from pcfm import _lib
+    feat, coords, res = cases.voxel_case(**kw)
+    feat2 = rng(kw["seed"] + 50).standard_normal(feat.shape).astype(np.float32)
+    vox, nc = gpu_voxel_coords(coords, res)
+    nc = nc.contiguous()
+    memo = be.plan_memo
+    memo.clear(); memo.enabled = True
+    h0, m0 = memo.hits, memo.misses
+    _lib.reset_launch_count()
+    out1, ind1, cnt1 = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res)
+    l1 = _lib.launch_count()
+    out2, ind2, cnt2 = be.pvcnn.avg_voxelize_forward(cu(feat2), vox, res)      # planned
+    l2 = _lib.launch_count() - l1
+    assert (memo.hits - h0, memo.misses - m0) == (1, 1) and l2 == 1 and l2 < l1
+    assert ind2 is ind1 and cnt2 is cnt1
+    memo.enabled = False
+    out2f, ind2f, cnt2f = be.pvcnn.avg_voxelize_forward(cu(feat2), vox, res)   # fresh build
+    memo.enabled = True
+    o_out2, o_ind, o_cnt = oracle.avg_voxelize_forward(feat2, host(vox), res)
+    assert_equal(host(ind2), o_ind, "ind"); assert_equal(host(cnt2), o_cnt, "cnt")
+    # cells of more than 16 points are summed in the plan's record order, which differs from build to build
+    assert_close(host(out2), host(out2f), "planned vs fresh avg_voxelize", atol_frac=1e-5)
+    assert_close(host(out2), o_out2, "planned avg_voxelize vs oracle", atol_frac=1e-5)
+    assert_close(host(out1), oracle.avg_voxelize_forward(feat, host(vox), res)[0], "first call", atol_frac=1e-5)
+
+    gy = rng(kw["seed"] + 60).standard_normal(feat.shape).astype(np.float32)
+    gy2 = rng(kw["seed"] + 61).standard_normal(feat.shape).astype(np.float32)
+    _, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, nc, out1)
+    _lib.reset_launch_count()
+    g1 = be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), nc, res)
+    l1 = _lib.launch_count()
+    g2 = be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy2), nc, res)       # planned
+    assert _lib.launch_count() - l1 == 1 and memo.hits - h0 == 2
+    want = oracle.trilinear_devoxelize_backward(gy2, host(inds), host(wgts), res)
+    assert_close(host(g2), want, "planned devoxelize backward vs oracle", atol_frac=1e-5)
+    assert_close(host(g1), oracle.trilinear_devoxelize_backward(gy, host(inds), host(wgts), res), "first", atol_frac=1e-5)
+
+
+def test_plan_memo_invalidation(be, oracle):
+    """A plan is valid for one coords tensor OBJECT at one version: an in-place write, another tensor with the same
+    values, another resolution or a cleared memo all rebuild."""
+    feat, coords, res = cases.voxel_case(seed=311, b=2, c=4, n=4000, res=16)
+    vox, _ = gpu_voxel_coords(coords, res)
+    memo = be.plan_memo
+    memo.clear(); memo.enabled = True
+    f = cu(feat)
+    be.pvcnn.avg_voxelize_forward(f, vox, res)
+    h = memo.hits
+    be.pvcnn.avg_voxelize_forward(f, vox.clone(), res); assert memo.hits == h       # other object
+    be.pvcnn.avg_voxelize_forward(f, vox, res); assert memo.hits == h + 1           # same object
+    vox.sub_(1).clamp_(0, res - 1)                                                  # in-place: version bump
+    out, ind, cnt = be.pvcnn.avg_voxelize_forward(f, vox, res); assert memo.hits == h + 1
+    o_out, o_ind, o_cnt = oracle.avg_voxelize_forward(feat, host(vox), res)
+    assert_equal(host(ind), o_ind, "ind after in-place edit"); assert_equal(host(cnt), o_cnt, "cnt")
+    assert_close(host(out), o_out, "out after in-place edit", atol_frac=1e-5)
+    out, ind, cnt = be.pvcnn.avg_voxelize_forward(f, vox, res); assert memo.hits == h + 2
+    assert_close(host(out), o_out, "planned after in-place edit", atol_frac=1e-5)
+    from pcfm import _lib
+    _lib.set_option("vox_fwd", 1)                                                   # generic variant: no cell plan kept
+    try:
+        be.pvcnn.avg_voxelize_forward(f, vox, res)
+        assert len(memo.entries) == 0
+        be.pvcnn.avg_voxelize_forward(f, vox, res); assert memo.hits == h + 2
+    finally:
+        _lib.set_option("vox_fwd", 0)
+
+
+def test_plan_reuse_through_autograd_two_blocks(be):
+    """Two PVConv-style blocks on one coords tensor, forward + backward through the autograd wrappers: identical
+    gradients with and without the plan memo, and the memo serves both the second forward and the second backward
+    (the backward runs on autograd's device thread, which keeps its own memo)."""
+    from pcfm import functional as F
+    from pcfm.nn import Voxelization
+    torch.manual_seed(5)
+    f0 = torch.randn(2, 8, 6000, device="cuda")
+    coords = torch.randn(2, 3, 6000, device="cuda")
+    w = torch.randn(2, 8, 6000, device="cuda")
+
+    def run(enabled):
+        be.plan_memo.clear(); be.plan_memo.enabled = enabled
+        f = f0.clone().requires_grad_(True)
+        vm = Voxelization(16, normalize=True, eps=1e-6)
+        x = f
+        for _ in range(2):
+            grid, nc = vm(x, coords)
+            x = F.trilinear_devoxelize(torch.tanh(grid), nc, 16, True) + x
+        (x * w).sum().backward()
+        torch.cuda.synchronize()
+        return host(x), host(f.grad)
+
+    try:
+        y_on, g_on = run(True)
+        y_off, g_off = run(False)
+    finally:
+        be.plan_memo.enabled = True
+    assert_close(y_on, y_off, "forward with / without plan reuse", rtol=1e-5, atol_frac=1e-5)
+    assert_close(g_on, g_off, "gradient with / without plan reuse", rtol=1e-5, atol_frac=1e-5)
 
 
 # ------------------------------------------------------------------------------------------------ randomized shapes
