@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(1024, 2)
         o[t] = acc;
       }
     } else {
-      const int t = cur.h.x, s0 = cur.h.y, n = cur.h.z;
-      const float rcp = __frcp_rn((float)n);
+      const int t = cur.h.x, s0 = cur.h.y, n = cur.h.z;   // n records in this piece, cur.h.w in the whole cell
+      const float rcp = __frcp_rn((float)cur.h.w);
       float acc = 0.f;
       for (int i = lane; i < n; i += 32 * PCFM_HEAVY_U) {  // PCFM_HEAVY_U independent record loads in flight per lane
         int p[PCFM_HEAVY_U];
@@ -145,7 +145,10 @@ __global__ void __launch_bounds__(1024, 2)
         }
       }
       acc = warp_sum(acc);
-      if (lane == 0) o[t] = acc;
+      if (lane == 0) {
+        if (n == cur.h.w) o[t] = acc;
+        else atomicAdd(o + t, acc);   // a piece of a split cell: the row was zeroed above (same CTA, before the barrier)
+      }
     }
     cur = nxt;
   }

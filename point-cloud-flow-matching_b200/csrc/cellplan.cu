@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(256) cp_layout_kernel(const int* __restrict__ 
     const int rb = recbase[(long long)b * t + v];
     for (int k = 0, o = 0; o < n; ++k, o += chunk)
       if (slot + k < hcap)
-        ((int4*)heavy)[(long long)b * hcap + slot + k] = make_int4(v, rb + o, min(chunk, n - o), mask);
+        ((int4*)heavy)[(long long)b * hcap + slot + k] = make_int4(v, rb + o, min(chunk, n - o), tri ? mask : n);
     return;
   }
   int j = lm - n;
@@ -359,7 +359,7 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
       const int mask = corner_mask(v, r, TRI);
       for (int k = 0, o = 0; o < c; ++k, o += chunk)
         if (slot + k < hcap)
-          ((int4*)heavy)[(long long)b * hcap + slot + k] = make_int4(v, rb + o, min(chunk, c - o), mask);
+          ((int4*)heavy)[(long long)b * hcap + slot + k] = make_int4(v, rb + o, min(chunk, c - o), TRI ? mask : c);
     }
   }
   if (q == 0)
@@ -409,7 +409,7 @@ static long long lcap_of(long long n, long long t) { return (((n < t ? n : t) + 
 
 size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear) {
   size_t s = 0;
-  const long long lcap = lcap_of(n, t), hcap = n / (kLightMaxMean + 1) + n / kHeavyChunk + 2, rcap = n + kEllPad;
+  const long long lcap = lcap_of(n, t), hcap = n / (kLightMaxMean + 1) + n / kHeavyChunkMean + 2, rcap = n + kEllPad;
   s += align256((size_t)b * lcap * 4) * 2 + align256((size_t)b * kCtr * 4);  // cells (+counters), slot0
   s += align256((size_t)b * kMetaInts * 4);                    // meta
   s += align256((size_t)b * hcap * 4 * 4);                     // heavy
@@ -429,8 +429,8 @@ struct PlanScratch {
 static bool cellplan_carve(bool tri, int b, int n, int t, CellPlan* plan, Workspace* ws, PlanScratch* sc) {
   plan->lcap = (int)lcap_of(n, t);
   plan->light_max = tri ? kLightMaxTri : kLightMaxMean;
-  plan->chunk = tri ? kHeavyChunk : 0x7fffffff;  // mean plans: the consumer stores a cell's mean, no pieces
-  plan->hcap = n / (plan->light_max + 1) + (tri ? n / kHeavyChunk : 0) + 2;
+  plan->chunk = tri ? kHeavyChunk : kHeavyChunkMean;
+  plan->hcap = n / (plan->light_max + 1) + n / plan->chunk + 2;
   plan->rcap = n + kEllPad;
   // cells and the counters are zeroed by ONE memset: they are carved from one block
   sc->zero_ints = (size_t)b * plan->lcap + (size_t)b * kCtr;

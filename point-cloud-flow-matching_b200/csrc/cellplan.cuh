@@ -4,7 +4,7 @@
 //   light cells (<= light_max points): sorted by point count (descending) and cut into slices of 32 cells; the i-th
 //       record of the 32 cells of a slice is contiguous (lane l reads rec[slot0 + 32*i]), so a warp walking 32 cells
 //       reads one coalesced line per step and pads only to the longest cell of its slice.
-//   heavy cells (> light_max points): records contiguous per cell, reduced by a whole warp.
+//   heavy cells (> light_max points): records contiguous per cell, reduced by a whole warp per piece of the cell.
 //
 // Records are 4 bytes (point id) for mean plans and 16 bytes (point id + the three trilinear fractions) for
 // trilinear plans.  In mean plans, cells of up to kSortMax points keep their records in ascending point order
@@ -22,6 +22,12 @@ constexpr int kLightMaxMean = 64;
 constexpr int kLightMaxTri = 64;
 constexpr int kHeavyChunk = 512;   // trilinear plans: a heavy cell is listed as pieces of at most this many records, so no
                                   // single warp owns a 2000-point cell (the pieces are combined with atomics anyway)
+#ifndef PCFM_HEAVY_CHUNK_MEAN
+#define PCFM_HEAVY_CHUNK_MEAN 512
+#endif
+constexpr int kHeavyChunkMean = PCFM_HEAVY_CHUNK_MEAN;  // mean plans: same, so that the 1500-point centre cells of a dense
+                                  // cloud on a small grid (r = 8) are not the serial tail of one warp; entry .w = the
+                                  // cell's total count (the divisor), pieces of a split cell are added with RED.ADD
 constexpr int kSortMax = 16;   // light cells up to this size keep their records in ascending point order
 constexpr int kMetaInts = 4;   // per batch element: [0] end of the light list (multiple of 32), [1] heavy cells
 
@@ -29,8 +35,8 @@ struct CellPlan {
   int* cells = nullptr;    // [B, lcap]  light cells, count-descending: (count << 24) | cell; 0 = hole
   int* slot0 = nullptr;    // [B, lcap]  (corner mask << 24) | first record slot (records are 32 slots apart)
   int* meta = nullptr;     // [B, kMetaInts]
-  int* heavy = nullptr;    // [B, hcap, 4]  {cell, first slot, count, corner mask} per heavy cell (mean plans) or per
-                           //               piece of <= kHeavyChunk records of a heavy cell (trilinear plans)
+  int* heavy = nullptr;    // [B, hcap, 4]  per piece of <= chunk records of a heavy cell: {cell, first slot, records in the
+                           //               piece, corner mask (trilinear plans) | records in the whole cell (mean plans)}
   void* rec = nullptr;     // [B, rcap] records
   int lcap = 0, hcap = 0, rcap = 0, light_max = 0, chunk = 0;
   bool pdl = false;        // built by the fused kernel, which releases dependent launches early (launch_dependent)

@@ -40,6 +40,8 @@ def main():
     ap.add_argument("--opt", default="", help="extra pcfm_set_option pairs, e.g. devox_rep=0,stage=1")
     ap.add_argument("--plan", type=int, default=0, help="pcfm_set_option('plan', .): 1 = multi-kernel cell-plan build")
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: r x N x C sweep (B=2)")
+    ap.add_argument("--memo", type=int, default=0, help="1: leave the cell-plan memo on for every op (repeated calls on "
+                    "the same coords then time the *_planned entries); default: off, planned entries timed as own ops")
     args = ap.parse_args()
     only = set(args.only.split(",")) if args.only else None
     ref = None
@@ -48,6 +50,7 @@ def main():
         ref = {k: build_ref.load_ref(k) for k in ("pvcnn", "chamfer", "emd", "chamfer6d")}
     dev = "cuda"
     _lib.set_option("plan", args.plan)
+    be.plan_memo.enabled = bool(args.memo)
     for kv in filter(None, args.opt.split(",")):
         _lib.set_option(kv.split("=")[0], int(kv.split("=")[1]))
     g = torch.Generator(device=dev).manual_seed(0)
@@ -87,6 +90,21 @@ def main():
             else (lambda: P.trilinear_devoxelize_backward(gy, inds, wgts, r)),
             "devox_bwd_generic": lambda: P.trilinear_devoxelize_backward(gy, inds, wgts, r),
         }
+        if not args.memo and r <= P.MAX_FAST_DEVOX_BWD_R:   # the second PVConv block of a stage: plan left by the first
+
+            def planned(fn):
+                def run():
+                    be.plan_memo.enabled = True
+                    fn()
+                    be.plan_memo.enabled = False
+                return run
+            be.plan_memo.enabled = True
+            be.plan_memo.clear()
+            ops["vox_fwd"](); ops["devox_bwd"]()      # builds the two plans the *_planned ops reuse
+            be.plan_memo.enabled = False
+            ops["vox_fwd_planned"] = planned(ops["vox_fwd"])
+            ops["devox_bwd_planned"] = planned(ops["devox_bwd"])
+            byt["vox_fwd_planned"], byt["devox_bwd_planned"] = byt["vox_fwd"], byt["devox_bwd"]
         if args.ops:
             ops = {k: v for k, v in ops.items() if k in args.ops.split(",")}
         for op, fn in ops.items():

@@ -103,6 +103,21 @@ def test_avg_voxelize(be, oracle, ref, kw, variant):
         assert_close(host(gx), host(ref["pvcnn"].avg_voxelize_backward(cu(gy), r_ind, r_cnt)), "grad vs reference")
 
 
+@pytest.mark.parametrize("n", [700, 20000])
+def test_avg_voxelize_all_points_in_few_voxels(be, oracle, n):
+    """Degenerate clouds: every point in ONE voxel (a single heavy cell, listed as pieces of <= 512 records that
+    several warps reduce and combine with RED.ADD) and every point in one of two voxels."""
+    r0 = rng(400 + n)
+    feat = r0.standard_normal((2, 5, n)).astype(np.float32)
+    vox = np.zeros((2, 3, n), np.int32)
+    vox[0] = 3                                   # cloud 0: one voxel
+    vox[1, 2] = r0.integers(0, 2, size=n)        # cloud 1: two voxels
+    out, ind, cnt = be.pvcnn.avg_voxelize_forward(cu(feat), cu(vox), 8)
+    o_out, o_ind, o_cnt = oracle.avg_voxelize_forward(feat, vox, 8)
+    assert_equal(host(ind), o_ind, "ind"); assert_equal(host(cnt), o_cnt, "cnt")
+    assert_close(host(out), o_out, "out", atol_frac=1e-5)
+
+
 def test_avg_voxelize_stage_variants_agree(be):
     from pcfm import _lib
     feat, coords, res = cases.voxel_case(seed=9, b=2, c=8, n=4000, res=16)
