@@ -19,6 +19,8 @@ extern int g_opt_devox_bwd;     // see pcfm_set_option
 extern int g_opt_vox_fwd;
 extern int g_opt_stage;
 extern int g_opt_devox_il;      // 1 = channel-interleaved planes in devoxelize forward when G >= 4 (default)
+extern int g_opt_devox_cl;      // devoxelize forward on small grids: 0 = point-lane kernels (default: measured faster),
+                                // 1 = channel-lane kernel for r <= 8, 2 = up to r = 10 (one CTA per SM)
 extern int g_opt_pdl;           // programmatic dependent launch: 0 = off, 1 = inside an operator (row kernel behind its
                                 // plan / index kernel), 2 = also between operators (every PVConv kernel waits at its
                                 // top, then releases the kernel behind it: launch + scheduling overlap the previous tail)

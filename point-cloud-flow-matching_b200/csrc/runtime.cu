@@ -17,6 +17,7 @@ int g_opt_gather_bwd = 0;
 int g_opt_fps = 0;
 int g_opt_pdl = 2;
 int g_opt_devox_il = 1;
+int g_opt_devox_cl = 0;
 int g_num_sms = 0;
 
 int num_sms() {
@@ -72,6 +73,7 @@ int pcfm_set_option(const char* key, int value) {
   if (!strcmp(key, "vox_fwd")) { pcfm::g_opt_vox_fwd = value; return 0; }
   if (!strcmp(key, "stage")) { pcfm::g_opt_stage = value; return 0; }
   if (!strcmp(key, "devox_il")) { pcfm::g_opt_devox_il = value; return 0; }
+  if (!strcmp(key, "devox_cl")) { pcfm::g_opt_devox_cl = value; return 0; }
   if (!strcmp(key, "pdl")) { pcfm::g_opt_pdl = value; return 0; }
   if (!strcmp(key, "fps")) { pcfm::g_opt_fps = value; return 0; }
   if (!strcmp(key, "gather_bwd")) { pcfm::g_opt_gather_bwd = value; return 0; }

@@ -168,6 +168,11 @@ DEVOX_SHAPES = [
     dict(seed=20, b=2, c=608, n=1000, res=8),     # four channels per CTA: channel-interleaved forward kernel <4,8>
     dict(seed=21, b=2, c=592, n=1500, res=16),    # <4,16>
     dict(seed=22, b=2, c=592, n=700, res=12),     # <4,runtime r>
+    dict(seed=27, b=1, c=32, n=2500, res=10),     # channel-lane kernel under devox_cl=2 (one CTA per SM)
+    dict(seed=23, b=2, c=32, n=20000, res=8),     # C % 32 == 0, r <= 8: also run through the optional channel-lane kernel
+    dict(seed=24, b=1, c=64, n=1001, res=5),      # same, odd point count and grid
+    dict(seed=25, b=2, c=32, n=5, res=2),         # same, fewer points than one warp step
+    dict(seed=26, b=3, c=96, n=4099, res=7),
 ]
 
 
@@ -183,6 +188,16 @@ def test_trilinear_devoxelize(be, oracle, ref, kw):
     e_outs, e_inds, e_wgts = be.pvcnn.trilinear_devoxelize_forward(res, False, cu(coords), cu(vox))
     assert tuple(e_inds.shape) == (1,) and tuple(e_wgts.shape) == (1,)     # trilinear_devox.cpp:45-49
     assert_equal(host(e_outs), host(outs), "eval-mode outs")
+    if kw["c"] % 32 == 0 and res <= 10:   # optional channel-lane kernel (devox.cu): 1 = up to r = 8, 2 = up to r = 10
+        for opt in (1, 2):
+            _lib.set_option("devox_cl", opt)
+            try:
+                p_outs, p_inds, p_wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(coords), cu(vox))
+            finally:
+                _lib.set_option("devox_cl", 0)
+            assert_equal(host(p_inds), o_inds, f"inds (devox_cl={opt})")
+            assert_equal(host(p_wgts), o_wgts, f"wgts (devox_cl={opt})")
+            assert_equal(host(p_outs), host(outs), f"outs (devox_cl={opt}): same FMA order in every forward kernel")
     o_gx = oracle.trilinear_devoxelize_backward(gy, o_inds, o_wgts, res)
     for variant in (0, 1):
         _lib.set_option("devox_bwd", variant)
