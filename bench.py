@@ -44,8 +44,10 @@ CONFIG = {
                 "(C,r) = 2x(128,32) 2x(256,16) 2x(256,8); vox fwd + devox fwd(train) + devox bwd + vox bwd per instance",
     "batch": B, "points": NPTS, "stages": STAGES,
     "plans": "the two PVConv blocks of a stage share one coords tensor (models.py:385-389), so the second block's "
-             "avg_voxelize forward / devoxelize backward reuse the first block's cell plan (pcfm_*_planned); the plan "
-             "memo is cleared at the start of EVERY step (new point clouds every training step): 6 plan builds per step",
+             "avg_voxelize forward / devoxelize backward reuse the first block's cell plans (pcfm_*_planned); the first "
+             "avg_voxelize of a stage builds the mean AND the trilinear plan in one launch "
+             "(pcfm_avg_voxelize_forward_dual, what pcfm.nn.Voxelization calls in a training pass); the plan memo is "
+             "cleared at the start of EVERY step (new point clouds every training step): 3 dual builds per step",
     "l2": "inputs larger than L2: ~4.8 GB touched per step, every primitive reads tensors not written in that step",
     "parallelism": "one process per GPU, replicas (data parallel), no data-path collective",
 }
@@ -287,7 +289,7 @@ def run_ours(args):
         for ch in chains:
             ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if rec is not None else None
             if ev: ev[0].record()
-            out, ind, cnt = P.avg_voxelize_forward(ch["feat"], ch["vox"], ch["r"])
+            out, ind, cnt = P.avg_voxelize_forward(ch["feat"], ch["vox"], ch["r"], ch["nc"])  # as pcfm.nn.Voxelization
             if ev: ev[1].record()
             outs, inds, wgts = P.trilinear_devoxelize_forward(ch["r"], True, ch["nc"], ch["conv_out"])
             if ev: ev[2].record()

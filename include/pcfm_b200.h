@@ -120,6 +120,16 @@ int pcfm_trilinear_devoxelize_backward_coords(const float* grad_y, const float* 
  * the two entries below take the workspace of an earlier call with identical (coords, b, n, r), untouched since, and
  * launch only the row kernel.  Results are those of the unplanned entries on the same coords.  The caller owns the
  * validity of the plan (pcfm/backend.py keys its memo on tensor identity + version + CUDA-graph capture + stream). */
+/* pcfm_avg_voxelize_forward that ALSO leaves the trilinear plan of `float_coords` (f32[B,3,N] in [0,r-1], the
+ * coordinates the PVConv block will devoxelize at, pvconv.py:35-37) in `tri_workspace`
+ * (pcfm_trilinear_devoxelize_backward_coords_workspace bytes), ready for pcfm_trilinear_devoxelize_backward_planned in
+ * the backward pass.  Both plans are built by one kernel: a single build is latency-bound on 8 CTAs per cloud, the
+ * second one runs beside it on idle SMs.  `workspace` afterwards holds the mean plan as after
+ * pcfm_avg_voxelize_forward. */
+int pcfm_avg_voxelize_forward_dual(const float* features, const int* coords, const float* float_coords, int b, int c,
+                                   int n, int r, float* out, int* ind, int* cnt, void* workspace,
+                                   size_t workspace_bytes, void* tri_workspace, size_t tri_workspace_bytes,
+                                   pcfm_stream_t stream);
 int pcfm_avg_voxelize_forward_planned(const float* features, int b, int c, int n, int r, float* out,
                                       const void* plan_workspace, size_t plan_workspace_bytes,
                                       pcfm_stream_t stream);

@@ -444,6 +444,23 @@ int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, i
   return launch_vox_fwd(features, plan, b, c, n, t, out, st, false);
 }
 
+int pcfm_avg_voxelize_forward_dual(const float* features, const int* coords, const float* float_coords, int b, int c,
+                                   int n, int r, float* out, int* ind, int* cnt, void* workspace,
+                                   size_t workspace_bytes, void* tri_workspace, size_t tri_workspace_bytes,
+                                   pcfm_stream_t stream) {
+  if (b < 0 || c < 0 || n < 0 || r <= 0 || (long long)r * r * r > (1 << 24)) return PCFM_E_BADARG;
+  if (b == 0) return 0;
+  if (!cnt || (c > 0 && !out) || (n > 0 && (!coords || !float_coords || !ind || (c > 0 && !features))))
+    return PCFM_E_BADARG;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int t = r * r * r;
+  Workspace ws(workspace, workspace_bytes), wst(tri_workspace, tri_workspace_bytes);
+  CellPlan plan, tri;
+  int rc = cellplan_build_dual(coords, float_coords, r, ind, b, n, t, cnt, &plan, &ws, &tri, &wst, st);
+  if (rc || c == 0) return rc;
+  return launch_vox_fwd(features, plan, b, c, n, t, out, st, false);
+}
+
 int pcfm_avg_voxelize_forward_planned(const float* features, int b, int c, int n, int r, float* out,
                                       const void* plan_workspace, size_t plan_workspace_bytes,
                                       pcfm_stream_t stream) {

@@ -225,25 +225,23 @@ constexpr int kH = kLightCap + 1, kHP = kLightCap + 2;
 __device__ __forceinline__ int cell_owner(int v) { return (v >> 5) % kCl; }
 __device__ __forceinline__ int cell_local(int v) { return (((v >> 5) / kCl) << 5) | (v & 31); }
 
+// `b` = cloud of this cluster, `tab` = [tq] this CTA's share of the per-cell table (dynamic shared memory)
 template <bool TRI>
-__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
-    cp_cluster_kernel(const int* __restrict__ vox_coords, const float* __restrict__ fcoords, int r,
-                      int* __restrict__ ind_out, int n, int t, int tq, int lm, int chunk,
-                      int* __restrict__ cnt_out,
-                      int* __restrict__ rank, int* __restrict__ cells, int* __restrict__ slot0,
-                      int* __restrict__ meta, int* __restrict__ heavy, void* __restrict__ rec, int lcap, int hcap,
-                      int rcap) {
-  griddep_wait();               // chained PDL: this kernel may itself have started before its predecessor finished
-  griddep_launch_dependents();  // the consumer kernel may start staging its rows now; it waits before reading the plan
+__device__ __forceinline__ void cp_cluster_body(const int* __restrict__ vox_coords, const float* __restrict__ fcoords,
+                                                int r, int* __restrict__ ind_out, int n, int t, int tq, int lm,
+                                                int chunk, int* __restrict__ cnt_out, int* __restrict__ rank,
+                                                int* __restrict__ cells, int* __restrict__ slot0,
+                                                int* __restrict__ meta, int* __restrict__ heavy,
+                                                void* __restrict__ rec, int lcap, int hcap, int rcap, const int b,
+                                                int* tab) {
   cg::cluster_group cluster = cg::this_cluster();
-  extern __shared__ int tab[];  // [tq] this CTA's share of the per-cell table
   __shared__ int bin[kNB];      // this CTA's histogram of cell sizes (read by the other CTAs in phase 3)
   __shared__ int pos[kNB];      // running positions inside this CTA's part of every bin
   __shared__ int off[kNB];      // where this CTA's part of every bin starts (sum over lower-ranked CTAs)
   __shared__ int tot[kNB];      // cluster-wide histogram
   __shared__ int P[kLightCap + 1], F[kLightCap + 1], Bs[kLightCap + 1];
   __shared__ int p_end;
-  const int q = (int)cluster.block_rank(), b = blockIdx.x / kCl;
+  const int q = (int)cluster.block_rank();
   const int tid = threadIdx.x, nt = blockDim.x;
   const long long base = (long long)b * n;
   const float* fb = TRI ? fcoords + base * 3 : nullptr;
@@ -402,6 +400,45 @@ __global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
   }
 }
 
+template <bool TRI>
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
+    cp_cluster_kernel(const int* __restrict__ vox_coords, const float* __restrict__ fcoords, int r,
+                      int* __restrict__ ind_out, int n, int t, int tq, int lm, int chunk,
+                      int* __restrict__ cnt_out,
+                      int* __restrict__ rank, int* __restrict__ cells, int* __restrict__ slot0,
+                      int* __restrict__ meta, int* __restrict__ heavy, void* __restrict__ rec, int lcap, int hcap,
+                      int rcap) {
+  griddep_wait();               // chained PDL: this kernel may itself have started before its predecessor finished
+  griddep_launch_dependents();  // the consumer kernel may start staging its rows now; it waits before reading the plan
+  extern __shared__ int tab[];
+  cp_cluster_body<TRI>(vox_coords, fcoords, r, ind_out, n, t, tq, lm, chunk, cnt_out, rank, cells, slot0, meta, heavy, rec,
+                       lcap, hcap, rcap, blockIdx.x / kCl, tab);
+}
+
+// Both plans of a PVConv stage in ONE launch: clusters [0, B) build the mean plan (voxel coordinates), clusters
+// [B, 2B) the trilinear plan (float coordinates).  One build is latency-bound on 8 CTAs per cloud (5-6 cluster
+// barriers) and leaves most SMs idle; the second one runs beside it for free.
+struct PlanOut {
+  int *rank, *cells, *slot0, *meta, *heavy;
+  void* rec;
+  int lcap, hcap, rcap, lm, chunk;
+};
+__global__ void __cluster_dims__(kCl, 1, 1) __launch_bounds__(kPlanThreads, 1)
+    cp_cluster_dual_kernel(const int* __restrict__ vox_coords, const float* __restrict__ fcoords, int r,
+                           int* __restrict__ ind_out, int* __restrict__ cnt_out, int n, int t, int tq, int nb,
+                           PlanOut pm, PlanOut pt) {
+  griddep_wait();
+  griddep_launch_dependents();
+  extern __shared__ int tab[];
+  const int cl = blockIdx.x / kCl;  // uniform over the cluster
+  if (cl < nb)
+    cp_cluster_body<false>(vox_coords, nullptr, r, ind_out, n, t, tq, pm.lm, pm.chunk, cnt_out, pm.rank, pm.cells,
+                           pm.slot0, pm.meta, pm.heavy, pm.rec, pm.lcap, pm.hcap, pm.rcap, cl, tab);
+  else
+    cp_cluster_body<true>(nullptr, fcoords, r, nullptr, n, t, tq, pt.lm, pt.chunk, nullptr, pt.rank, pt.cells, pt.slot0,
+                          pt.meta, pt.heavy, pt.rec, pt.lcap, pt.hcap, pt.rcap, cl - nb, tab);
+}
+
 constexpr size_t kFusedMaxTable = 220 * 1024;  // per CTA; + ~2 KB static shared memory <= 227 KB
 constexpr int kFusedMaxPoints = 1 << 18;       // beyond this 8 CTAs per cloud are slower than the multi-kernel build
 
@@ -512,6 +549,33 @@ int cellplan_build(const int* vox_coords, const float* float_coords, int r, int*
       PCFM_LAUNCHED();
     }
   }
+  return 0;
+}
+
+
+int cellplan_build_dual(const int* vox_coords, const float* float_coords, int r, int* ind_out, int b, int n, int t,
+                        int* cnt, CellPlan* pm, Workspace* wsm, CellPlan* pt, Workspace* wst, cudaStream_t st) {
+  const int tq = (cdiv(cdiv(t, 32), kCl)) * 32;
+  const size_t tab_bytes = (size_t)tq * sizeof(int);
+  const bool fused = g_opt_plan == 0 && n > 0 && n <= kFusedMaxPoints && tab_bytes <= kFusedMaxTable;
+  if (!fused) {  // two separate builds
+    int rc = cellplan_build(vox_coords, nullptr, r, ind_out, b, n, t, cnt, pm, wsm, st);
+    if (rc) return rc;
+    return cellplan_build(nullptr, float_coords, r, nullptr, b, n, t, nullptr, pt, wst, st);
+  }
+  PlanScratch sm, stt;
+  if (!cellplan_carve(false, b, n, t, pm, wsm, &sm) || !cellplan_carve(true, b, n, t, pt, wst, &stt))
+    return PCFM_E_WORKSPACE;
+  PlanOut om = {sm.rank, pm->cells, pm->slot0, pm->meta, pm->heavy, pm->rec, pm->lcap, pm->hcap, pm->rcap,
+                pm->light_max, pm->chunk};
+  PlanOut ot = {stt.rank, pt->cells, pt->slot0, pt->meta, pt->heavy, pt->rec, pt->lcap, pt->hcap, pt->rcap,
+                pt->light_max, pt->chunk};
+  PCFM_CUDA(allow_dyn_smem((const void*)cp_cluster_dual_kernel, (int)kFusedMaxTable));
+  PCFM_CUDA(launch_dependent(cp_cluster_dual_kernel, dim3(2 * b * kCl), dim3(kPlanThreads), tab_bytes, st,
+                             g_opt_pdl >= 2, vox_coords, float_coords, r, ind_out, cnt, n, t, tq, b, om, ot));
+  PCFM_LAUNCHED();
+  pm->pdl = g_opt_pdl != 0;
+  pt->pdl = false;  // its consumer runs much later (the backward pass), behind other kernels
   return 0;
 }
 

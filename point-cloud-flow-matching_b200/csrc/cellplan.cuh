@@ -56,6 +56,11 @@ size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear)
 int cellplan_build(const int* vox_coords, const float* float_coords, int r, int* ind_out, int b, int n, int t,
                    int* cnt, CellPlan* plan, Workspace* ws, cudaStream_t st);
 
+// Mean plan (vox_coords -> ind_out, cnt, *pm in *wsm) and trilinear plan (float_coords -> *pt in *wst) of the same
+// clouds by ONE kernel when the fused build applies, else by two builds.
+int cellplan_build_dual(const int* vox_coords, const float* float_coords, int r, int* ind_out, int b, int n, int t,
+                        int* cnt, CellPlan* pm, Workspace* wsm, CellPlan* pt, Workspace* wst, cudaStream_t st);
+
 // Re-attaches to the plan that an earlier cellplan_build() with the same (kind, b, n, t) left in `ws` (same buffer,
 // untouched since): no kernel is launched.  The plan is valid for exactly the coordinates it was built from.
 int cellplan_attach(bool trilinear, int b, int n, int t, CellPlan* plan, Workspace* ws);

@@ -34,6 +34,7 @@ SIGNATURES = {
     "pcfm_trilinear_devoxelize_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_trilinear_devoxelize_backward_coords_workspace": (_sz, [_i, _i, _i, _i]),
     "pcfm_trilinear_devoxelize_backward_coords": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_avg_voxelize_forward_dual": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p, _sz, _p]),
     "pcfm_avg_voxelize_forward_planned": (_i, [_p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_trilinear_devoxelize_backward_planned": (_i, [_p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_ball_query": (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _p]),

@@ -55,15 +55,17 @@ def _chk(x, name, kind):
     (_check_float if kind == "f" else _check_int)(x, name)
 
 
-class _PlanMemo(threading.local):
-    """Per-thread memo of cell plans (include/pcfm_b200.h, "Plan reuse"), keyed on the coordinate tensor.
+class _PlanMemo:
+    """Memo of cell plans (include/pcfm_b200.h, "Plan reuse"), keyed on the coordinate tensor.
 
     The PVConv blocks of one ContextNet stage voxelize / devoxelize at the SAME coords tensor and resolution
     (models.py:385-389; pcfm.nn.Voxelization hands every block of a stage the same (norm_coords, vox_coords) tensor
-    objects), so the plan built by the first avg_voxelize_forward serves the second, and the plan built by the first
-    trilinear_devoxelize_backward_coords of the backward pass serves the second.  An entry is valid only for the same
-    tensor OBJECT (held by weak reference, so a recycled address cannot alias) with the same autograd version
-    counter, shape, resolution, stream and CUDA-graph capture.  `plan_memo.enabled = False` switches it off;
+    objects), so the plan built by the first avg_voxelize_forward serves the second, and the trilinear plan — built
+    beside the mean plan when the forward pass announces the float coordinates, else by the first
+    trilinear_devoxelize_backward_coords — serves both backward calls.  An entry is valid only for the same tensor
+    OBJECT (held by weak reference, so a recycled address cannot alias) with the same autograd version counter, shape,
+    resolution, stream and CUDA-graph capture.  One memo for all threads (the backward pass runs on autograd's device
+    thread and uses plans the forward thread built), guarded by a lock.  `plan_memo.enabled = False` switches it off;
     `plan_memo.clear()` drops every plan (a write through `.data` or a raw pointer bypasses the version counter).
     """
 
@@ -73,6 +75,7 @@ class _PlanMemo(threading.local):
         self.enabled = True
         self.entries = {}  # key -> (weakref(coords), version, payload); insertion order = age
         self.hits = self.misses = 0
+        self._lock = threading.Lock()
 
     @staticmethod
     def _key(kind, coords, r):
@@ -84,26 +87,31 @@ class _PlanMemo(threading.local):
         if not self.enabled:
             return None
         key = self._key(kind, coords, r)
-        e = self.entries.get(key)
-        if e is not None and e[0]() is coords and e[1] == coords._version:
-            self.hits += 1
-            return e[2]
-        if e is not None:
-            del self.entries[key]
-        self.misses += 1
+        with self._lock:
+            e = self.entries.get(key)
+            if e is not None and e[0]() is coords and e[1] == coords._version:
+                self.hits += 1
+                return e[2]
+            if e is not None:
+                del self.entries[key]
+            self.misses += 1
         return None
 
     def put(self, kind, coords, r, payload):
         if not self.enabled:
             return
-        for k in [k for k, e in self.entries.items() if e[0]() is None]:  # coords tensor died
-            del self.entries[k]
-        while len(self.entries) >= self.CAPACITY:
-            del self.entries[next(iter(self.entries))]
-        self.entries[self._key(kind, coords, r)] = (weakref.ref(coords), coords._version, payload)
+        key = self._key(kind, coords, r)
+        with self._lock:
+            for k in [k for k, e in self.entries.items() if e[0]() is None]:  # coords tensor died
+                del self.entries[k]
+            self.entries.pop(key, None)
+            while len(self.entries) >= self.CAPACITY:
+                del self.entries[next(iter(self.entries))]
+            self.entries[key] = (weakref.ref(coords), coords._version, payload)
 
     def clear(self):
-        self.entries.clear()
+        with self._lock:
+            self.entries.clear()
 
 
 plan_memo = _PlanMemo()
@@ -115,7 +123,10 @@ class _PvcnnBackend:
 
     # ---- voxelization (vox.cpp:17-43, 54-76) ----
     @staticmethod
-    def avg_voxelize_forward(features, coords, resolution):
+    def avg_voxelize_forward(features, coords, resolution, float_coords=None):
+        """vox.cpp:17-43.  `float_coords` (extension, optional): the float voxel coordinates the block will devoxelize
+        at; when given and no plan is memoised yet, the trilinear plan of the backward pass is built by the same
+        kernel as the mean plan (pcfm_avg_voxelize_forward_dual) and memoised for trilinear_devoxelize_backward_coords."""
         _chk(features, "features", "f")
         _chk(coords, "coords", "i")
         b, c, n = features.shape
@@ -135,10 +146,23 @@ class _PvcnnBackend:
             cnt = torch.empty((b, s), dtype=torch.int32, device=dev)
             nb = lib.pcfm_avg_voxelize_forward_workspace(b, c, n, r)
             ws = _ws(nb, dev)
-            check(lib.pcfm_avg_voxelize_forward(_ptr(features), _ptr(coords), b, c, n, r, _ptr(out), _ptr(ind),
-                                                _ptr(cnt), _ptr(ws), ws.numel(), _stream(features)),
-                  "avg_voxelize_forward")
-            if n > 0 and c > 0 and _lib.options.get("vox_fwd", 0) == 0:  # generic variants leave no cell plan
+            memo_ok = n > 0 and c > 0 and _lib.options.get("vox_fwd", 0) == 0  # generic variants leave no cell plan
+            if (float_coords is not None and memo_ok and plan_memo.enabled
+                    and plan_memo.get("tri", float_coords, r) is None):
+                _chk(float_coords, "float_coords", "f")
+                if tuple(float_coords.shape) != (b, 3, n):
+                    raise RuntimeError("float_coords must be [B,3,N]")
+                wst = _ws(lib.pcfm_trilinear_devoxelize_backward_coords_workspace(b, c, n, r), dev)
+                check(lib.pcfm_avg_voxelize_forward_dual(_ptr(features), _ptr(coords), _ptr(float_coords), b, c, n, r,
+                                                         _ptr(out), _ptr(ind), _ptr(cnt), _ptr(ws), ws.numel(),
+                                                         _ptr(wst), wst.numel(), _stream(features)),
+                      "avg_voxelize_forward_dual")
+                plan_memo.put("tri", float_coords, r, wst)
+            else:
+                check(lib.pcfm_avg_voxelize_forward(_ptr(features), _ptr(coords), b, c, n, r, _ptr(out), _ptr(ind),
+                                                    _ptr(cnt), _ptr(ws), ws.numel(), _stream(features)),
+                      "avg_voxelize_forward")
+            if memo_ok:
                 plan_memo.put("mean", coords, r, (ws, ind, cnt))
         return [out, ind, cnt]
 

@@ -17,14 +17,17 @@ __all__ = ["avg_voxelize", "trilinear_devoxelize", "ball_query", "grouping", "ga
 
 
 class AvgVoxelization(Function):
-    """features f32[B,C,N], coords (integer voxel coords) [B,3,N], resolution -> f32[B,C,R,R,R]."""
+    """features f32[B,C,N], coords (integer voxel coords) [B,3,N], resolution[, float_coords] -> f32[B,C,R,R,R]."""
 
     @staticmethod
-    def forward(ctx, features, coords, resolution):
+    def forward(ctx, features, coords, resolution, float_coords=None):
         feats = features.contiguous()
         vox = coords.int().contiguous()
         r = int(resolution)
-        out, ind, cnt = _backend.avg_voxelize_forward(feats, vox, r)
+        # float_coords (extension, what pcfm.nn.Voxelization passes): where the block will devoxelize; when a backward
+        # pass will follow, its trilinear cell plan is built by the same kernel as the plan of this call
+        fc = float_coords if (float_coords is not None and ctx.needs_input_grad[0]) else None
+        out, ind, cnt = _backend.avg_voxelize_forward(feats, vox, r, fc)
         ctx.save_for_backward(ind, cnt)
         return out.view(feats.shape[0], feats.shape[1], r, r, r)
 
@@ -33,7 +36,7 @@ class AvgVoxelization(Function):
         ind, cnt = ctx.saved_tensors
         b, c = grad_output.shape[0], grad_output.shape[1]
         flat = grad_output.contiguous().view(b, c, -1)
-        return _backend.avg_voxelize_backward(flat, ind, cnt), None, None
+        return _backend.avg_voxelize_backward(flat, ind, cnt), None, None, None
 
 
 class TrilinearDevoxelization(Function):

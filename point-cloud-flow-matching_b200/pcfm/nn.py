@@ -87,6 +87,8 @@ class Voxelization(nn.Module):
 
     def forward(self, features, coords):
         nc, vox = self._coords(coords)
+        if nc.is_cuda and nc.dtype == torch.float32 and nc.is_contiguous():
+            return F.avg_voxelize(features, vox, self.r, nc), nc   # nc: lets a training pass build both cell plans at once
         return F.avg_voxelize(features, vox, self.r), nc
 
     def extra_repr(self):

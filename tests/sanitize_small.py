@@ -38,6 +38,20 @@ def main():
             _lib.set_option("stage", stage)
             be.pvcnn.trilinear_devoxelize_backward_coords(rn(b, c, n), fc, r)
         _lib.set_option("stage", 0)
+    # plan reuse (second call on the same coords tensors -> *_planned entries), incl. heavy cells split into pieces,
+    # and the optional channel-lane devoxelize kernel (C % 32 == 0, r <= 10)
+    be.plan_memo.clear()
+    for (b, c, n, r) in [(2, 32, 3001, 8), (1, 64, 5000, 5), (1, 32, 700, 10), (1, 32, 4000, 40)]:
+        vc = torch.randint(0, min(r, 3), (b, 3, n), device="cuda", dtype=torch.int32, generator=g)   # dense: heavy cells
+        fc = (torch.rand(b, 3, n, device="cuda", generator=g) * (r - 1)).contiguous()
+        h0 = be.plan_memo.hits
+        for _ in range(2):
+            out, ind, cnt = be.pvcnn.avg_voxelize_forward(rn(b, c, n), vc, r)
+            be.pvcnn.trilinear_devoxelize_backward_coords(rn(b, c, n), fc, r)
+        assert be.plan_memo.hits - h0 == 2
+        for opt in (1, 2, 0):
+            _lib.set_option("devox_cl", opt)
+            be.pvcnn.trilinear_devoxelize_forward(r, True, fc, out)
     # plane too large for shared memory (r = 40 -> 64000 floats): L2 path
     be.pvcnn.trilinear_devoxelize_forward(40, True, torch.rand(1, 3, 500, device="cuda") * 39, rn(1, 2, 64000))
     pts = torch.rand(2, 3, 700, device="cuda", generator=g)

@@ -825,6 +825,42 @@ def test_plan_reuse_matches_fresh_build(be, oracle, kw):
     assert_close(host(g1), oracle.trilinear_devoxelize_backward(gy, host(inds), host(wgts), res), "first", atol_frac=1e-5)
 
 
+@pytest.mark.parametrize("kw", PLAN_SHAPES, ids=lambda k: f"b{k['b']}c{k['c']}n{k['n']}r{k['res']}")
+def test_dual_plan_build(be, oracle, kw):
+    """pcfm_avg_voxelize_forward_dual: the first avg_voxelize of a training stage is told where the block will
+    devoxelize and builds the trilinear plan of the backward pass beside its own (one launch); the backward then runs
+    on that plan.  Same results as the separate builds / the oracle."""
+    from pcfm import _lib
+    feat, coords, res = cases.voxel_case(**kw)
+    vox, nc = gpu_voxel_coords(coords, res)
+    nc = nc.contiguous()
+    memo = be.plan_memo
+    memo.clear(); memo.enabled = True
+    _lib.reset_launch_count()
+    out, ind, cnt = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res, nc)
+    assert _lib.launch_count() == 2                      # dual plan kernel + row kernel (fused build: all PLAN_SHAPES)
+    o_out, o_ind, o_cnt = oracle.avg_voxelize_forward(feat, host(vox), res)
+    assert_equal(host(ind), o_ind, "ind"); assert_equal(host(cnt), o_cnt, "cnt")
+    assert_close(host(out), o_out, "out", atol_frac=1e-5)
+    gy = rng(kw["seed"] + 70).standard_normal(feat.shape).astype(np.float32)
+    _, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, nc, out)
+    h0 = memo.hits
+    _lib.reset_launch_count()
+    g = be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), nc, res)
+    assert memo.hits == h0 + 1 and _lib.launch_count() == 1     # the row kernel only
+    assert_close(host(g), oracle.trilinear_devoxelize_backward(gy, host(inds), host(wgts), res),
+                 "devoxelize backward on the plan built in the forward pass", atol_frac=1e-5)
+    _lib.set_option("plan", 1)                           # multi-kernel build: dual falls back to two builds
+    try:
+        memo.clear()
+        out2, ind2, cnt2 = be.pvcnn.avg_voxelize_forward(cu(feat), vox, res, nc)
+        g2 = be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), nc, res)
+    finally:
+        _lib.set_option("plan", 0)
+    assert_equal(host(ind2), o_ind, "ind (multi-kernel)"); assert_close(host(out2), o_out, "out (multi-kernel)", atol_frac=1e-5)
+    assert_close(host(g2), host(g), "grad (multi-kernel)", rtol=1e-5, atol_frac=1e-5)
+
+
 def test_plan_memo_invalidation(be, oracle):
     """A plan is valid for one coords tensor OBJECT at one version: an in-place write, another tensor with the same
     values, another resolution or a cleared memo all rebuild."""
@@ -873,8 +909,11 @@ def test_plan_reuse_through_autograd_two_blocks(be):
         for _ in range(2):
             grid, nc = vm(x, coords)
             x = F.trilinear_devoxelize(torch.tanh(grid), nc, 16, True) + x
+        h0 = be.plan_memo.hits
         (x * w).sum().backward()
         torch.cuda.synchronize()
+        if enabled:   # both devoxelize backwards run on the trilinear plan the forward pass built (other thread)
+            assert be.plan_memo.hits - h0 == 2
         return host(x), host(f.grad)
 
     try:
