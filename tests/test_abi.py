@@ -60,6 +60,14 @@ def test_workspace_queries_are_host_only(built):
     # argument validation happens before any CUDA call
     assert l.pcfm_avg_voxelize_forward(None, None, 1, 1, 1, 0, None, None, None, None, 0, None) == -1
     assert l.pcfm_chamfer3d_allpairs(None, None, 1, 1, 0, 0, None, None) == -1
+    # plan-reuse entries: no plan workspace / no coordinates -> PCFM_E_BADARG, empty problems -> 0, all without CUDA
+    assert l.pcfm_avg_voxelize_forward_planned(None, 1, 1, 1, 8, None, None, 0, None) == -1
+    assert l.pcfm_trilinear_devoxelize_backward_planned(None, 1, 1, 1, 8, None, None, 0, None) == -1
+    assert l.pcfm_avg_voxelize_forward_planned(None, 0, 4, 100, 8, None, None, 0, None) == 0
+    assert l.pcfm_trilinear_devoxelize_backward_planned(None, 2, 0, 100, 8, None, None, 0, None) == 0
+    assert l.pcfm_avg_voxelize_forward_dual(None, None, None, 1, 1, 1, 8, None, None, None, None, 0, None, 0, None) == -1
+    assert l.pcfm_avg_voxelize_forward_dual(None, None, None, 1, 1, 1, 300, None, None, None, None, 0, None, 0, None) == -1
+    assert l.pcfm_set_option(b"devox_cl", 0) == 0
     assert l.pcfm_set_option(b"nonsense", 1) == -1
     assert l.pcfm_set_option(b"stage", 0) == 0
 
