@@ -147,11 +147,12 @@ class _PvcnnBackend:
             nb = lib.pcfm_avg_voxelize_forward_workspace(b, c, n, r)
             ws = _ws(nb, dev)
             memo_ok = n > 0 and c > 0 and _lib.options.get("vox_fwd", 0) == 0  # generic variants leave no cell plan
-            if (float_coords is not None and memo_ok and plan_memo.enabled
-                    and plan_memo.get("tri", float_coords, r) is None):
+            if float_coords is not None:
                 _chk(float_coords, "float_coords", "f")
                 if tuple(float_coords.shape) != (b, 3, n):
                     raise RuntimeError("float_coords must be [B,3,N]")
+            if (float_coords is not None and memo_ok and plan_memo.enabled
+                    and plan_memo.get("tri", float_coords, r) is None):
                 wst = _ws(lib.pcfm_trilinear_devoxelize_backward_coords_workspace(b, c, n, r), dev)
                 check(lib.pcfm_avg_voxelize_forward_dual(_ptr(features), _ptr(coords), _ptr(float_coords), b, c, n, r,
                                                          _ptr(out), _ptr(ind), _ptr(cnt), _ptr(ws), ws.numel(),
