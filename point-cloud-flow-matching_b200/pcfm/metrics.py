@@ -4,6 +4,7 @@
   chamfer_{2,5,6}DFunction / chamfer_{2,5,6}DDist   <- ChamferDistancePytorch/chamfer6D/dist_chamfer_6D.py:30-82 (and 2D, 5D)
   EarthMoverDistanceFunction / earth_mover_distance <- PyTorchEMD/emd.py:6-51
   earth_mover_distance_nograd                       <- PyTorchEMD/emd_nograd.py:7-44
+  fscore                                            <- ChamferDistancePytorch/fscore.py:3-16
 Inputs are cast to float32 under autocast exactly like the reference's custom_fwd(cast_inputs=float32).
 """
 import torch
@@ -159,3 +160,16 @@ def earth_mover_distance(xyz1, xyz2, transpose=True):
 def earth_mover_distance_nograd(xyz1, xyz2, transpose=True):
     xyz1, xyz2 = _emd_prepare(xyz1, xyz2, transpose)
     return EarthMoverDistanceFunctionNoGrad.apply(xyz1, xyz2) / float(xyz1.shape[1])
+
+
+def fscore(dist1, dist2, threshold=0.001):
+    """F-score of two clouds from the Chamfer outputs (ChamferDistancePytorch/fscore.py:3-16).
+
+    dist1 [B,N], dist2 [B,M]: SQUARED nearest-neighbour distances as returned by chamfer_3DDist, so `threshold` is a
+    squared distance too.  Returns (fscore [B], precision_1 [B], precision_2 [B]): the fraction of points of each
+    cloud closer than the threshold to the other cloud and their harmonic mean (0 where both fractions are 0).
+    """
+    hit1 = dist1.lt(threshold).to(torch.float32).mean(dim=1)
+    hit2 = dist2.lt(threshold).to(torch.float32).mean(dim=1)
+    f = 2 * hit1 * hit2 / (hit1 + hit2)
+    return torch.nan_to_num(f, nan=0.0), hit1, hit2

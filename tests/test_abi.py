@@ -123,3 +123,17 @@ def test_product_does_not_import_oracle():
                 if re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M) or "/root/reference" in txt:
                     bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_fscore_matches_the_reference_definition(built):
+    """ChamferDistancePytorch/fscore.py:3-16: precision = share of squared NN distances below the threshold,
+    F = harmonic mean, 0 (not NaN) where neither cloud has a hit."""
+    import torch
+    from pcfm.metrics import fscore
+    d1 = torch.tensor([[0.0, 0.5e-3, 2e-3, 1.0], [1.0, 1.0, 1.0, 1.0]])
+    d2 = torch.tensor([[0.0, 1e-4], [0.5, 2.0]])
+    f, p1, p2 = fscore(d1, d2)
+    assert torch.allclose(p1, torch.tensor([0.5, 0.0])) and torch.allclose(p2, torch.tensor([1.0, 0.0]))
+    assert torch.allclose(f, torch.tensor([2 * 0.5 * 1.0 / 1.5, 0.0]))
+    f2, _, _ = fscore(d1, d2, threshold=10.0)
+    assert torch.equal(f2, torch.ones(2))
