@@ -85,6 +85,7 @@ def test_dropin_import_trees(built):
         from third_party.PyTorchEMD.emd import earth_mover_distance
         from third_party.PyTorchEMD.backend import emd_cuda_dynamic
         from third_party.PyTorchEMD.emd_nograd import earth_mover_distance_nograd
+        from fscore import fscore                  # ChamferDistancePytorch/fscore.py
     finally:
         sys.path.pop(0)
     for name in ["avg_voxelize_forward", "avg_voxelize_backward", "trilinear_devoxelize_forward",
