@@ -1,7 +1,10 @@
 """Per-op timing table (CUDA events) of the new kernels and, when oracle/_ref is built, of the UNMODIFIED reference
 CUDA kernels on the same GPU and inputs.  Test/measurement infrastructure:
-    python tests/perf_ops.py [--ref] [--only s1,chamfer] [--kind randn|uniform]
-Writes gpurun_out/perf_ops_<kind>.json."""
+    python tests/perf_ops.py [--ref] [--only s1,chamfer] [--kind randn|uniform] [--ops vox_fwd,...] [--opt key=value,...]
+Every op is a fresh call (the cell-plan memo is off unless --memo 1); `vox_fwd_planned` / `devox_bwd_planned` time the
+same ops on a plan left by an earlier call, i.e. the second PVConv block of a stage.  --opt forwards pcfm_set_option
+pairs for A/B runs (e.g. devox_cl=1); PCFM_B200_LIB selects a variant library built by tests/build_variant.sh.
+Writes gpurun_out/perf_ops_<kind>.json.  See also tests/perf_sampler.py (config 3)."""
 import argparse
 import json
 import os
