@@ -218,8 +218,8 @@ def run_reference_arm(args):
     batch = B
     while batch > 1 and probe * (batch / 2) * (args.steps + args.warmup) > budget:
         batch //= 2
-    for _ in range(args.warmup):
-        cpu_chain_step(torch, tc, feats, coords, batch)
+    for _ in range(args.warmup + 2):   # + 2: the first passes of a fresh process page in the thread pool and the
+        cpu_chain_step(torch, tc, feats, coords, batch)   # allocator arenas (an outlier of 4x was seen without them)
     t0 = time.perf_counter()
     pts = 0
     for _ in range(args.steps):
@@ -233,6 +233,130 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(line), file=_JSON_OUT, flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def check_against_oracle(torch, P, be, chains, nch=4):
+    """Warm-up check of the timed kernels at the FULL bench shapes: the first `nch` channels of one chain per stage shape
+    against the C oracle (oracle/pcfm_oracle.c) — every (batch, channel) row is an independent problem, so a channel
+    slice of the full-size call is checked exactly.  Asserts indices bit-exact and values within 1e-5 (normwise)."""
+    import numpy as np
+    from oracle import cpu_ref
+    cpu_ref.build()
+    worst, rows = 0.0, []
+
+    def rel(a, b):
+        a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+        return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+    for ch in chains[::2]:
+        c, r = ch["c"], ch["r"]
+        be.plan_memo.clear()
+        out, ind, cnt = P.avg_voxelize_forward(ch["feat"], ch["vox"], r, ch["nc"])
+        outs, inds, wgts = P.trilinear_devoxelize_forward(r, True, ch["nc"], ch["conv_out"])
+        ggrid = P.trilinear_devoxelize_backward_coords(ch["gy"], ch["nc"], r)
+        gfeat = P.avg_voxelize_backward(ch["gconv"], ind, cnt)
+        h = lambda t: t.detach().cpu().numpy()  # noqa: E731
+        o_out, o_ind, o_cnt = cpu_ref.avg_voxelize_forward(h(ch["feat"][:, :nch].contiguous()), h(ch["vox"]), r)
+        o_outs, o_inds, o_wgts = cpu_ref.trilinear_devoxelize_forward(r, h(ch["nc"]), h(ch["conv_out"][:, :nch].contiguous()))
+        o_gg = cpu_ref.trilinear_devoxelize_backward(h(ch["gy"][:, :nch].contiguous()), o_inds, o_wgts, r)
+        o_gf = cpu_ref.avg_voxelize_backward(h(ch["gconv"][:, :nch].contiguous()), o_ind, o_cnt)
+        assert np.array_equal(h(ind), o_ind) and np.array_equal(h(cnt), o_cnt), "voxel indices / counts"
+        assert np.array_equal(h(inds), o_inds) and np.array_equal(h(wgts), o_wgts), "trilinear indices / weights"
+        errs = {"vox_fwd": rel(h(out[:, :nch]), o_out), "devox_fwd": rel(h(outs[:, :nch]), o_outs),
+                "devox_bwd": rel(h(ggrid[:, :nch]), o_gg), "vox_bwd": rel(h(gfeat[:, :nch]), o_gf)}
+        for k, e in errs.items():
+            assert e <= 1e-5, f"bench warm-up: {k} C={c} r={r} differs from the oracle by {e:.3e}"
+        worst = max(worst, max(errs.values()))
+        rows.append({"C": c, "r": r, **{k: float(f"{e:.2e}") for k, e in errs.items()}})
+    return {"checked": "first %d channels of one chain per stage shape at the full bench sizes vs the C oracle: voxel / "
+                       "trilinear indices, counts, weights bit-exact; values normwise" % nch,
+            "max_rel_err": float(f"{worst:.2e}"), "tolerance": 1e-5, "per_shape": rows}
+
+
+def dp_training_step(torch, dist, dev, rank, world, barrier, max_over_ranks, _lib, steps=6):
+    """BASELINE config 2 as train.py runs it: the reference's HybridMLP (models.py:604-694, imported UNMODIFIED from
+    baseline/_ref/models.py; its PVConv / SharedMLP imports are served by dropin/) wrapped in DistributedDataParallel
+    exactly like train.py:241-244, per-GPU batch 8 x 20000 RGB points, cond = latent 128 + 1; one step = forward, MSE
+    flow-matching loss (train.py:604-640), backward with the bucketed gradient all-reduce, AdamW step."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import refmodel
+    if not refmodel.staged():
+        return {"unavailable": "baseline/_ref/models.py not staged (python __graft_entry__.py build)"}
+    net = refmodel.make_hybrid(dev).train()
+    nparam = sum(p.numel() for p in net.parameters())
+    model = net
+    if world > 1:
+        from torch.nn.parallel import DistributedDataParallel as DDP
+        model = DDP(net, device_ids=[dev.index], output_device=dev.index, broadcast_buffers=False,
+                    find_unused_parameters=False)                                   # train.py:241-244
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=0.0)
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    data = torch.rand(B, NPTS, 6, device=dev, generator=g) * 2 - 1
+    cond = torch.randn(B, 129, device=dev, generator=g)
+
+    def one_step():
+        z = torch.randn(B, NPTS, 6, device=dev, generator=g)
+        t = torch.rand(B, device=dev, generator=g)
+        x_t = (1.0 - t)[:, None, None] * z + t[:, None, None] * data
+        opt.zero_grad(set_to_none=True)
+        loss = torch.nn.functional.mse_loss(model(x_t, t, cond), data - z)
+        loss.backward()
+        opt.step()
+        return loss
+
+    for _ in range(3):
+        one_step()
+    barrier()
+    _lib.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one_step()
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    out = {"model": "HybridMLP from the unmodified reference models.py (defaults: stages (128,256,256) x 2 blocks, "
+                    "r = (32,16,8)), point_dim 6, cond_dim 129",
+           "parallelism": f"DistributedDataParallel x{world}" if world > 1 else "single GPU (no all-reduce)",
+           "per_gpu_batch": B, "points": NPTS, "parameters": nparam,
+           "grad_allreduce_bytes_per_step": nparam * 4 if world > 1 else 0,
+           "ms_per_step": ms, "mpts_per_s": B * NPTS * world / ms / 1e3, "scaling": "weak",
+           "pcfm_launches_per_step": _lib.launch_count() / steps, "loss": float(loss), "steps": steps}
+    del model, net, opt
+    return out
+
+
+def time_reference_cuda(torch, chains):
+    """BASELINE.md column 2: the UNMODIFIED reference CUDA kernels (oracle/_ref/pvcnn) on the same chains, same GPU."""
+    from oracle import build_ref
+    R = build_ref.load_ref("pvcnn")
+    if R is None:
+        return {"unavailable": "oracle/_ref/pvcnn not built"}
+
+    def ref_step():
+        for ch in chains:
+            r = ch["r"]
+            out, ind, cnt = R.avg_voxelize_forward(ch["feat"], ch["vox"], r)
+            outs, inds, wgts = R.trilinear_devoxelize_forward(r, True, ch["nc"], ch["conv_out"])
+            R.trilinear_devoxelize_backward(ch["gy"], inds, wgts, r)
+            R.avg_voxelize_backward(ch["gconv"], ind, cnt)
+
+    ref_step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # the reference launches on the legacy default stream (SURVEY 2.3): events recorded there bracket its kernels
+    legacy = torch.cuda.default_stream()
+    e0.record(legacy)
+    n_it = 2
+    for _ in range(n_it):
+        ref_step()
+    e1.record(legacy)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n_it
+    return {"ms_per_step": ms, "value": len(chains) * B * NPTS / ms / 1e3, "unit": UNIT, "steps": n_it,
+            "what": "third_party/pvcnn kernels compiled unmodified for sm_100a (oracle/build_ref.py), same chains, same "
+                    "resident inputs, this GPU"}
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -303,6 +427,9 @@ def run_ours(args):
 
     step()
     barrier()
+    oracle_check = None
+    if rank == 0 and not args.no_oracle_check:
+        oracle_check = check_against_oracle(torch, P, be, chains)
     sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(max(args.warmup, 3) + 60):   # >= W warm-up steps (~0.2 s), under the clock sampler
         step()
@@ -420,6 +547,7 @@ def run_ours(args):
     d2h = sum(ho.numel() * 4 for ho in h_out)
     e2e = {"value": pts_per_step / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
            "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+           "pcie_GBps_each_way": {"h2d": h2d / e2e_s / 1e9, "d2h": d2h / e2e_s / 1e9},
            "pinned_on_cpus": ("GPU-local " + str(len(numa.cpus)) + " of " + str(os.cpu_count())) if numa.cpus else "all",
            "api": "pcfm.nn.Voxelization + pcfm.functional.trilinear_devoxelize + autograd backward; pinned host tensors "
                   "in and out every step, uploads / kernels / downloads on three streams, two steps in flight"}
@@ -471,6 +599,9 @@ def run_ours(args):
             module = {"error": repr(e)}
 
     # ---------------- all-pairs CD / EMD (config 4 shapes), rows sharded over ranks ----------------
+    # Timed region = what an evaluation run does: the reference set arrives SHARDED over the ranks and is
+    # all-gathered (24.6 MB), every rank computes its block of rows with the all-pairs kernels, and the row blocks are
+    # all-gathered into the full matrix on every rank (4 MB) - both collectives inside the CUDA-event window.
     allpairs = None
     try:
         if args.skip_allpairs:
@@ -479,28 +610,64 @@ def run_ours(args):
         gg = torch.Generator(device=dev).manual_seed(7)
         S = torch.randn(1000, 2048, 3, device=dev, generator=gg) * 0.3
         R = torch.randn(1000, 2048, 3, device=dev, generator=gg) * 0.3
-        lo, hi = ev.shard_range(1000, rank, world)
-        be.chamfer3d_allpairs(S[lo:lo + 8], R[:64]); barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        rlo, rhi = ev.shard_range(1000, rank, world)
+        R_local = R[rlo:rhi].contiguous()          # this rank's shard of the reference set
+        r_counts = [h - l for l, h in (ev.shard_range(1000, k, world) for k in range(world))]
+        del R
+        be.chamfer3d_allpairs(S[:8], S[:64])
+        ev.all_gather_clouds(R_local[:2].contiguous(), [2] * world); barrier()
+        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
         a0.record()
-        cd = ev.pairwise_matrix(S[lo:hi], R, "cd", block=250)
-        a1.record(); barrier()
-        cd_ms = max_over_ranks(a0.elapsed_time(a1))
-        nref_emd = 16                                           # bounded EMD sample: 1000 x 16 pairs
-        be.emd_allpairs(S[lo:lo + 2], R[:2]); barrier()
+        R = ev.all_gather_clouds(R_local, r_counts)                          # collective 1: reference set
+        a1.record()
+        cd = ev.pairwise_matrix_sharded(S, R, "cd", block=250, gather=True)  # kernels + collective 2: row blocks
+        a2.record(); barrier()
+        cd_ms = max_over_ranks(a0.elapsed_time(a2))
+        gather_ms = max_over_ranks(a0.elapsed_time(a1))
+        full_emd = world >= 8 or args.full_emd
+        nref_emd = 1000 if full_emd else 16                     # N < 8: bounded EMD sample (1000 x 16 pairs)
+        be.emd_allpairs(S[:2], R[:2]); barrier()
         a0.record()
-        emd = ev.pairwise_matrix(S[lo:hi], R[:nref_emd], "emd", block=250)
+        emd = ev.pairwise_matrix_sharded(S, R[:nref_emd].contiguous(), "emd", block=250, gather=True)
         a1.record(); barrier()
         emd_ms = max_over_ranks(a0.elapsed_time(a1))
+        # the complete metric set on the CD matrices (MMD / COV / 1-NNA: S x R, and S x S, R x R as symmetric halves)
+        a0.record()
+        metrics = ev.compute_metrics(S, R, metrics=("cd",), block=250)
+        a1.record(); barrier()
+        metrics_ms = max_over_ranks(a0.elapsed_time(a1))
         allpairs = {"scaling": "strong", "clouds": "1000 x 1000 x 2048 pts (config 4)",
-                    "cd_pairs_per_s": 1000 * 1000 / (cd_ms * 1e-3), "cd_ms": cd_ms,
+                    "timed": "all-gather of the sharded reference set + all-pairs kernels on this rank's row block + "
+                             "all-gather of the row blocks (full matrix on every rank); CUDA events, max over ranks",
+                    "cd_pairs_per_s": 1000 * 1000 / (cd_ms * 1e-3), "cd_ms": cd_ms, "ref_all_gather_ms": gather_ms,
+                    "ref_all_gather_bytes": 1000 * 2048 * 3 * 4, "matrix_all_gather_bytes": 1000 * 1000 * 4,
                     "cd_evals_per_s": 1000 * 1000 * 2048 * 2048 / (cd_ms * 1e-3),
                     "emd_pairs_per_s": 1000 * nref_emd / (emd_ms * 1e-3), "emd_ms": emd_ms,
-                    "emd_sample": f"1000 x {nref_emd} pairs", "cd_checksum": float(cd.double().sum()),
-                    "emd_checksum": float(emd.double().sum())}
+                    "emd_sample": f"1000 x {nref_emd} pairs" + (" (the full matrix)" if full_emd else ""),
+                    "cd_checksum": float(cd.double().sum()), "emd_checksum": float(emd.double().sum()),
+                    "cd_metrics": metrics["cd"], "cd_metrics_ms": metrics_ms,
+                    "cd_metrics_pairs": 1000 * 1000 + 2 * (1000 * 1001 // 2),
+                    "cd_metrics_note": "S x R in full, S x S and R x R as symmetric matrices (upper-triangle blocks, "
+                                       "half the pairs), blocks of 250 rows"}
         del S, R, cd, emd
     except Exception as e:  # noqa: BLE001
         allpairs = {"error": repr(e)}
+
+    # ---------------- data-parallel training step of the reference's own model (config 2) ----------------
+    dp = None
+    if not args.skip_dp:
+        try:
+            dp = dp_training_step(torch, dist, dev, rank, world, barrier, max_over_ranks, _lib)
+        except Exception as e:  # noqa: BLE001
+            dp = {"error": repr(e)}
+        torch.cuda.empty_cache()
+
+    ref_cuda = None
+    if rank == 0 and world == 1 and not args.no_reference_cuda:
+        try:
+            ref_cuda = time_reference_cuda(torch, chains)
+        except Exception as e:  # noqa: BLE001
+            ref_cuda = {"error": repr(e)}
 
     # ---------------- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----------------
     cpu = None
@@ -523,7 +690,7 @@ def run_ours(args):
                 "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": CONFIG, "clocks": clocks,
                 "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu, "allpairs": allpairs, "pvconv_modules": module,
-                "lib": _lib.build_info()}
+                "dp_step": dp, "reference_cuda": ref_cuda, "oracle_check": oracle_check, "lib": _lib.build_info()}
         print(json.dumps(line), file=_JSON_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -551,6 +718,10 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--skip-allpairs", action="store_true", help="profiling runs: PVConv primitives only")
     ap.add_argument("--skip-module", action="store_true", help="skip the module-level (cuDNN included) measurement")
+    ap.add_argument("--skip-dp", action="store_true", help="skip the data-parallel training step of the reference model")
+    ap.add_argument("--no-reference-cuda", action="store_true", help="skip timing the reference CUDA kernels (oracle/_ref)")
+    ap.add_argument("--no-oracle-check", action="store_true", help="skip the warm-up check against the CPU oracle")
+    ap.add_argument("--full-emd", action="store_true", help="the full 1000 x 1000 EMD matrix also below 8 GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

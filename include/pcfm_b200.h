@@ -49,7 +49,9 @@ unsigned long long pcfm_stream_capture_id(pcfm_stream_t stream);
 /* Tuning knob: "variant" selects alternative kernel implementations for A/B measurement.
  * key: "devox_bwd" (generic inds/wgts entry: 0 = sorted-segment gather [default], 1 = global RED atomics),
  *      "vox_fwd"   (0 = cell plan [default], 1 = global RED atomics, 2 = generic sorted-segment gather),
- *      "stage"     (0 = TMA bulk staging where aligned [default], 1 = plain ld/st staging). */
+ *      "stage"     (0 = TMA bulk staging where aligned [default], 1 = plain ld/st staging),
+ *      "devox_fwd" (host-side choice read by pcfm/backend.py: 0 = cell-plan walk where supported [default],
+ *                   1 = plane-staging point-lane kernels). */
 int pcfm_set_option(const char* key, int value);
 
 /* ------------------------------------------------------------------------------------------------
@@ -69,7 +71,9 @@ int pcfm_voxel_coords(const float* centred, const float* scale, int b, int n, in
 /* avg_voxelize_forward (vox.cpp:17-43): features f32[B,C,N], coords i32[B,3,N] (already voxel integers in
  * [0,r-1]) -> out f32[B,C,r^3], ind i32[B,N] (= x*r^2+y*r+z), cnt i32[B,r^3].
  * out[b,c,v] = sum over points with ind==v of features*(1/cnt[v]); empty voxels are 0.
- * The sum runs in ascending point order (one legal ordering of the reference's atomics) => deterministic. */
+ * The sum runs in ascending point order (one legal ordering of the reference's atomics) => deterministic.
+ * Limits of the cell plan (24-bit fields): r <= 256 and N below ~16.7 million points per cloud; beyond them this entry,
+ * the _dual / _planned entries and the trilinear *_coords / *_planned / *_cells entries return PCFM_E_BADARG. */
 size_t pcfm_avg_voxelize_forward_workspace(int b, int c, int n, int r);
 int pcfm_avg_voxelize_forward(const float* features, const int* coords, int b, int c, int n, int r,
                               float* out, int* ind, int* cnt,
@@ -136,6 +140,22 @@ int pcfm_avg_voxelize_forward_planned(const float* features, int b, int c, int n
 int pcfm_trilinear_devoxelize_backward_planned(const float* grad_y, int b, int c, int n, int r, float* grad_x,
                                                const void* plan_workspace, size_t plan_workspace_bytes,
                                                pcfm_stream_t stream);
+
+/* trilinear_devoxelize_forward (trilinear_devox.cpp:18-55) as a walk over the trilinear cell plan: same outputs as
+ * pcfm_trilinear_devoxelize_forward (outs within rounding: the 8 products are summed along z, y, x instead of in
+ * corner order; inds / wgts bit-identical).  The points are visited cell by cell, so the 8 corner values of a cell are
+ * read once per cell and channel, and the output row leaves shared memory with one bulk store.
+ * `workspace`: pcfm_trilinear_devoxelize_backward_coords_workspace(b, c, n, r) bytes.  planned == 0: the plan of
+ * `coords` is built into it first (and stays there for pcfm_trilinear_devoxelize_backward_planned and later calls
+ * with planned == 1); planned != 0: it already holds the plan of the same (coords, b, n, r) — left by this entry,
+ * pcfm_avg_voxelize_forward_dual or pcfm_trilinear_devoxelize_backward_coords — and `coords` is read only for
+ * inds / wgts (may be NULL when is_training == 0).
+ * pcfm_trilinear_devoxelize_forward_cells_ok: 1 when this entry supports the shape (the output row of N floats must
+ * fit in shared memory: N <= 57k; 24-bit plan fields), else 0 — use pcfm_trilinear_devoxelize_forward. */
+int pcfm_trilinear_devoxelize_forward_cells_ok(int b, int c, int n, int r);
+int pcfm_trilinear_devoxelize_forward_cells(const float* coords, const float* features, int b, int c, int n, int r,
+                                            int is_training, float* outs, int* inds, float* wgts, void* workspace,
+                                            size_t workspace_bytes, int planned, pcfm_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Ball query / grouping / gather / FPS / 3-NN  (src/ball_query, src/grouping, src/sampling,

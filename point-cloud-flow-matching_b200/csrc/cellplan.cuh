@@ -6,9 +6,17 @@
 //       reads one coalesced line per step and pads only to the longest cell of its slice.
 //   heavy cells (> light_max points): records contiguous per cell, reduced by a whole warp per piece of the cell.
 //
-// Records are 4 bytes (point id) for mean plans and 16 bytes (point id + the three trilinear fractions) for
-// trilinear plans.  In mean plans, cells of up to kSortMax points keep their records in ascending point order
-// (deterministic sums, the order the oracle uses).
+// Mean plans: a record is a 4-byte point id; cells of up to kSortMax points keep their records in ascending point
+// order (deterministic sums, the order the oracle uses); a heavy cell's records start on a 16-byte boundary and are
+// padded to a multiple of 4 with the id N (the consumer keeps an exact zero at row[N]), so a lane reads 4 ids at once.
+//
+// Trilinear plans: the unit is a PAIR of points, stored as two float4 (structure of arrays over pair slots):
+//     recA[slot] = {off0, off1, fx0, fx1}     recB[slot] = {fy0, fy1, fz0, fz1}
+// off = 4 * point id (the byte offset into a channel row), f* = the trilinear fractions.  One 16-byte load per array
+// yields two points whose fractions sit in aligned register pairs, so the whole weight / accumulate arithmetic of the
+// consumers issues as packed fp32 (FADD2 / FMUL2 / FFMA2: two points per instruction).  A cell with an odd number of
+// points ends in a dummy half {off = 4*N, fractions 0}: the consumer keeps an exact zero (or a scratch slot) at row[N].
+// Light cells are binned by their number of pairs; the i-th pair of the 32 cells of a slice is contiguous.
 #pragma once
 #include "common.cuh"
 
@@ -18,9 +26,18 @@ namespace pcfm {
 // slot per point-lane but serialises a cell; warp-per-cell adds ~100 warp instructions per cell.  Measured on B200
 // (N=20000, r=8..32, warps taking work items dynamically): 64 beats 16, 32 and 128 for both plan kinds.
 constexpr int kLightCap = 64;      // upper bound of light_max (<= 255: 8-bit count field of CellPlan::cells)
-constexpr int kLightMaxMean = 64;
-constexpr int kLightMaxTri = 64;
-constexpr int kHeavyChunk = 512;   // trilinear plans: a heavy cell is listed as pieces of at most this many records, so no
+#ifndef PCFM_LIGHT_MAX_MEAN
+#define PCFM_LIGHT_MAX_MEAN 64
+#endif
+#ifndef PCFM_LIGHT_MAX_TRI
+#define PCFM_LIGHT_MAX_TRI 64
+#endif
+#ifndef PCFM_HEAVY_CHUNK_TRI
+#define PCFM_HEAVY_CHUNK_TRI 512
+#endif
+constexpr int kLightMaxMean = PCFM_LIGHT_MAX_MEAN;   // even, <= kLightCap
+constexpr int kLightMaxTri = PCFM_LIGHT_MAX_TRI;     // even, <= kLightCap
+constexpr int kHeavyChunk = PCFM_HEAVY_CHUNK_TRI;   // trilinear plans: a heavy cell is listed as pieces of at most this many records, so no
                                   // single warp owns a 2000-point cell (the pieces are combined with atomics anyway)
 #ifndef PCFM_HEAVY_CHUNK_MEAN
 #define PCFM_HEAVY_CHUNK_MEAN 512
@@ -37,15 +54,63 @@ struct CellPlan {
   int* meta = nullptr;     // [B, kMetaInts]
   int* heavy = nullptr;    // [B, hcap, 4]  per piece of <= chunk records of a heavy cell: {cell, first slot, records in the
                            //               piece, corner mask (trilinear plans) | records in the whole cell (mean plans)}
-  void* rec = nullptr;     // [B, rcap] records
+  void* rec = nullptr;     // [B, rcap] records (mean: int point ids; trilinear: float4 recA, see above)
+  void* rec2 = nullptr;    // [B, rcap] trilinear plans: float4 recB
   int lcap = 0, hcap = 0, rcap = 0, light_max = 0, chunk = 0;
   bool pdl = false;        // built by the fused kernel, which releases dependent launches early (launch_dependent)
 };
 
-struct TriRec {  // 16-byte record of a trilinear plan
-  int p;
-  float fx, fy, fz;
+// A work item of the cell kernels and its header, fetched ONE ITEM AHEAD so that the header's L2 latency overlaps the
+// previous item's work: light slice -> x = cells entry, y = slot0 entry of this lane's cell; heavy piece -> the int4.
+struct CellItem {
+  int item;
+  int4 h;
 };
+__device__ __forceinline__ CellItem next_cell_item(int* counter, int nslice, int nitem, const int* __restrict__ cl,
+                                                   const int* __restrict__ sl, const int4* __restrict__ hv) {
+  const int lane = threadIdx.x & 31;
+  CellItem c;
+  c.item = 0;
+  if (lane == 0) c.item = atomicAdd(counter, 1);
+  c.item = __shfl_sync(0xffffffffu, c.item, 0);
+  c.h = make_int4(0, 0, 0, 0);
+  if (c.item < nslice) {
+    c.h.x = cl[(c.item << 5) | lane];
+    c.h.y = sl[(c.item << 5) | lane];
+  } else if (c.item < nitem) {
+    c.h = hv[c.item - nslice];
+  }
+  return c;
+}
+
+// packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2, every lane rounded like the scalar instruction)
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pk2(float lo, float hi) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk2(f32x2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t sub2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+
+// false when the plan's packed fields cannot hold this problem (24-bit record slots and cell ids)
+bool cellplan_fits(long long n, long long t, bool trilinear);
 
 size_t cellplan_workspace_bytes(int b, long long n, long long t, bool trilinear);
 

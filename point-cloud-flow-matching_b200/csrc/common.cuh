@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <stddef.h>
 
 #include "../../include/pcfm_b200.h"
@@ -14,7 +15,8 @@ namespace pcfm {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-extern int64_t g_launches;      // kernels launched by this library (pcfm_launch_count)
+extern std::atomic<int64_t> g_launches;  // kernels launched by this library (pcfm_launch_count); the forward thread and
+                                         // autograd's device threads both launch
 extern int g_opt_devox_bwd;     // see pcfm_set_option
 extern int g_opt_vox_fwd;
 extern int g_opt_stage;
@@ -26,6 +28,8 @@ extern int g_opt_pdl;           // programmatic dependent launch: 0 = off, 1 = i
                                 // top, then releases the kernel behind it: launch + scheduling overlap the previous tail)
 extern int g_opt_fps;           // 0 = cluster FPS (points in registers) when the cloud fits, 1 = one CTA per cloud
 extern int g_opt_gather_bwd;    // 0 = gather backward with atomics (like the reference), 1 = sorted-segment sums
+extern int g_opt_devox_fwd;     // 0 = devoxelize forward as a walk over the trilinear cell plan when the caller offers a
+                                // workspace (default), 1 = always the plane-staging point-lane kernels
 extern int g_opt_plan;          // 0 = fused cell-plan build when it fits, 1 = always the multi-kernel build
 extern int g_num_sms;           // cached SM count of the current device (148 on B200)
 int num_sms();
@@ -35,7 +39,7 @@ cudaError_t allow_dyn_smem(const void* func, int bytes);
 
 #define PCFM_LAUNCHED()                                   \
   do {                                                    \
-    ++::pcfm::g_launches;                                 \
+    ::pcfm::g_launches.fetch_add(1, std::memory_order_relaxed); \
     cudaError_t e__ = cudaGetLastError();                 \
     if (e__ != cudaSuccess) return (int)e__;              \
   } while (0)

@@ -8,11 +8,12 @@
 #include "common.cuh"
 
 namespace pcfm {
-int64_t g_launches = 0;
+std::atomic<int64_t> g_launches{0};
 int g_opt_devox_bwd = 0;
 int g_opt_vox_fwd = 0;
 int g_opt_stage = 0;
 int g_opt_plan = 0;
+int g_opt_devox_fwd = 0;
 int g_opt_gather_bwd = 0;
 int g_opt_fps = 0;
 int g_opt_pdl = 2;
@@ -54,8 +55,8 @@ const char* pcfm_build_info(void) {
   return "pcfm_b200 abi1 sm_100a nvcc " PCFM_STR(__CUDACC_VER_MAJOR__) "." PCFM_STR(__CUDACC_VER_MINOR__);
 }
 
-int64_t pcfm_launch_count(void) { return pcfm::g_launches; }
-void pcfm_reset_launch_count(void) { pcfm::g_launches = 0; }
+int64_t pcfm_launch_count(void) { return pcfm::g_launches.load(std::memory_order_relaxed); }
+void pcfm_reset_launch_count(void) { pcfm::g_launches.store(0, std::memory_order_relaxed); }
 
 unsigned long long pcfm_stream_capture_id(pcfm_stream_t stream) {
   cudaStreamCaptureStatus status = cudaStreamCaptureStatusNone;
@@ -78,6 +79,7 @@ int pcfm_set_option(const char* key, int value) {
   if (!strcmp(key, "fps")) { pcfm::g_opt_fps = value; return 0; }
   if (!strcmp(key, "gather_bwd")) { pcfm::g_opt_gather_bwd = value; return 0; }
   if (!strcmp(key, "plan")) { pcfm::g_opt_plan = value; return 0; }
+  if (!strcmp(key, "devox_fwd")) { pcfm::g_opt_devox_fwd = value; return 0; }
   return PCFM_E_BADARG;
 }
 

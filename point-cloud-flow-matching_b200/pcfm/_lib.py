@@ -37,6 +37,8 @@ SIGNATURES = {
     "pcfm_avg_voxelize_forward_dual": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _p, _sz, _p]),
     "pcfm_avg_voxelize_forward_planned": (_i, [_p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_trilinear_devoxelize_backward_planned": (_i, [_p, _i, _i, _i, _i, _p, _p, _sz, _p]),
+    "pcfm_trilinear_devoxelize_forward_cells_ok": (_i, [_i, _i, _i, _i]),
+    "pcfm_trilinear_devoxelize_forward_cells": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p, _p, _p, _sz, _i, _p]),
     "pcfm_ball_query": (_i, [_p, _p, _i, _i, _i, _f, _i, _p, _p]),
     "pcfm_grouping_forward": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "pcfm_grouping_backward_workspace": (_sz, [_i, _i, _i, _i, _i]),

@@ -55,6 +55,15 @@ def _chk(x, name, kind):
     (_check_float if kind == "f" else _check_int)(x, name)
 
 
+def _version(t):
+    """Autograd version counter of a tensor, or None when it has none (tensors created under torch.inference_mode()
+    do not track versions): such tensors are simply not memoised."""
+    try:
+        return t._version
+    except RuntimeError:
+        return None
+
+
 class _PlanMemo:
     """Memo of cell plans (include/pcfm_b200.h, "Plan reuse"), keyed on the coordinate tensor.
 
@@ -86,10 +95,13 @@ class _PlanMemo:
     def get(self, kind, coords, r):
         if not self.enabled:
             return None
+        ver = _version(coords)
+        if ver is None:
+            return None
         key = self._key(kind, coords, r)
         with self._lock:
             e = self.entries.get(key)
-            if e is not None and e[0]() is coords and e[1] == coords._version:
+            if e is not None and e[0]() is coords and e[1] == ver:
                 self.hits += 1
                 return e[2]
             if e is not None:
@@ -100,6 +112,9 @@ class _PlanMemo:
     def put(self, kind, coords, r, payload):
         if not self.enabled:
             return
+        ver = _version(coords)
+        if ver is None:
+            return
         key = self._key(kind, coords, r)
         with self._lock:
             for k in [k for k, e in self.entries.items() if e[0]() is None]:  # coords tensor died
@@ -107,7 +122,7 @@ class _PlanMemo:
             self.entries.pop(key, None)
             while len(self.entries) >= self.CAPACITY:
                 del self.entries[next(iter(self.entries))]
-            self.entries[key] = (weakref.ref(coords), coords._version, payload)
+            self.entries[key] = (weakref.ref(coords), ver, payload)
 
     def clear(self):
         with self._lock:
@@ -218,6 +233,27 @@ class _PvcnnBackend:
             inds = torch.zeros((1,), dtype=torch.int32, device=dev)
             wgts = torch.zeros((1,), dtype=torch.float32, device=dev)
         with torch.cuda.device(dev):
+            # Walk over the trilinear cell plan (pcfm_trilinear_devoxelize_forward_cells): the plan is the one the
+            # block's avg_voxelize built beside its mean plan (pcfm.nn.Voxelization announces the float coordinates),
+            # and it serves the backward pass as well.  Without a memoised plan the walk pays for a build, which is
+            # only worth it for more than a few channels.
+            ws = None
+            if (c > 0 and n > 0 and _lib.options.get("devox_fwd", 0) == 0
+                    and lib.pcfm_trilinear_devoxelize_forward_cells_ok(b, c, n, r)):
+                ws = plan_memo.get("tri", coords, r)
+                planned = ws is not None
+                if not planned and c >= 16:
+                    ws = _ws(lib.pcfm_trilinear_devoxelize_backward_coords_workspace(b, c, n, r), dev)
+            if ws is not None:
+                check(lib.pcfm_trilinear_devoxelize_forward_cells(_ptr(coords), _ptr(features), b, c, n, r,
+                                                                  1 if is_training else 0, _ptr(outs),
+                                                                  _ptr(inds) if is_training else None,
+                                                                  _ptr(wgts) if is_training else None, _ptr(ws),
+                                                                  ws.numel(), 1 if planned else 0, _stream(features)),
+                      "trilinear_devoxelize_forward_cells")
+                if not planned:
+                    plan_memo.put("tri", coords, r, ws)
+                return [outs, inds, wgts]
             check(lib.pcfm_trilinear_devoxelize_forward(_ptr(coords), _ptr(features), b, c, n, r,
                                                         1 if is_training else 0, _ptr(outs),
                                                         _ptr(inds) if is_training else None,
@@ -391,11 +427,36 @@ class _PvcnnBackend:
         return grad_x
 
 
+def _chk_chamfer(dim, xyz, per_point, idx, grads=()):
+    """The reference reads every tensor through `.data<float>()` / `.data<int>()` (chamfer3D.cu:139-143), which raises
+    on a dtype mismatch; shapes are taken from xyz1 / xyz2 only.  Here the raw pointers go to the C ABI, so dtype,
+    device, contiguity and the shapes the kernels assume are checked first."""
+    x1, x2 = xyz
+    _chk(x1, "xyz1", "f")
+    _chk(x2, "xyz2", "f")
+    if x1.dim() != 3 or x2.dim() != 3 or x1.shape[2] != dim or x2.shape[2] != dim or x1.shape[0] != x2.shape[0]:
+        raise RuntimeError(f"chamfer_{dim}D: expected xyz1 [B,N,{dim}] and xyz2 [B,M,{dim}], got "
+                           f"{tuple(x1.shape)} {tuple(x2.shape)}")
+    for t, x, name in zip(per_point, xyz, ("dist1", "dist2")):
+        _chk(t, name, "f")
+        if t.numel() != x.shape[0] * x.shape[1]:
+            raise RuntimeError(f"chamfer_{dim}D: {name} must have B*N elements")
+    for t, x, name in zip(idx, xyz, ("idx1", "idx2")):
+        _chk(t, name, "i")
+        if t.numel() != x.shape[0] * x.shape[1]:
+            raise RuntimeError(f"chamfer_{dim}D: {name} must have B*N elements")
+    for t, x, name in zip(grads, xyz, ("gradxyz1", "gradxyz2")):
+        _chk(t, name, "f")
+        if t.numel() != x.numel():
+            raise RuntimeError(f"chamfer_{dim}D: {name} must match its cloud")
+
+
 class _Chamfer3D:
     """`chamfer_3D` (chamfer_cuda.cpp:30-33): caller-allocated outputs, returns 1 on success / 0 on CUDA error."""
 
     @staticmethod
     def forward(xyz1, xyz2, dist1, dist2, idx1, idx2):
+        _chk_chamfer(3, (xyz1, xyz2), (dist1, dist2), (idx1, idx2))
         b, n, _ = xyz1.shape
         m = xyz2.shape[1]
         with torch.cuda.device(xyz1.device):
@@ -408,6 +469,7 @@ class _Chamfer3D:
 
     @staticmethod
     def backward(xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2):
+        _chk_chamfer(3, (xyz1, xyz2), (graddist1, graddist2), (idx1, idx2), (gradxyz1, gradxyz2))
         b, n, _ = xyz1.shape
         m = xyz2.shape[1]
         with torch.cuda.device(xyz1.device):
@@ -427,10 +489,9 @@ class _ChamferND:
         self.dim = dim
 
     def forward(self, xyz1, xyz2, dist1, dist2, idx1, idx2):
+        _chk_chamfer(self.dim, (xyz1, xyz2), (dist1, dist2), (idx1, idx2))
         b, n, d = xyz1.shape
         m = xyz2.shape[1]
-        if d != self.dim or xyz2.shape[2] != self.dim:
-            raise RuntimeError(f"chamfer_{self.dim}D: last dimension must be {self.dim}")
         with torch.cuda.device(xyz1.device):
             rc = lib.pcfm_chamfer_nd_forward(_ptr(xyz1), _ptr(xyz2), b, n, m, d, _ptr(dist1), _ptr(dist2),
                                              _ptr(idx1), _ptr(idx2), _stream(xyz1))
@@ -440,6 +501,7 @@ class _ChamferND:
         return 1
 
     def backward(self, xyz1, xyz2, gradxyz1, gradxyz2, graddist1, graddist2, idx1, idx2):
+        _chk_chamfer(self.dim, (xyz1, xyz2), (graddist1, graddist2), (idx1, idx2), (gradxyz1, gradxyz2))
         b, n, d = xyz1.shape
         m = xyz2.shape[1]
         with torch.cuda.device(xyz1.device):

@@ -14,8 +14,8 @@ and to all-gather the finished row blocks.
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "all_gather_clouds", "pairwise_matrix", "pairwise_matrix_sharded", "mmd_cov", "one_nna",
-           "compute_metrics"]
+__all__ = ["shard_range", "all_gather_clouds", "pairwise_matrix", "pairwise_matrix_sharded",
+           "symmetric_matrix_sharded", "mmd_cov", "one_nna", "compute_metrics"]
 
 
 def shard_range(n, rank, world):
@@ -49,9 +49,46 @@ def all_gather_clouds(local, counts=None, group=None):
     return torch.cat([b[:k] for b, k in zip(bufs, counts)], dim=0)
 
 
+def _batched_pairs(metric):
+    """Pair function on the batched OPERATORS (chamfer_3D.forward / approxmatch + matchcost, one batch per row cloud):
+    for clouds beyond the limits of the all-pairs kernels (Chamfer: 8192 points in the second set; EMD: both clouds
+    resident in shared memory, ~5k points each).  Same values, without the one-CTA-per-pair kernels' speed."""
+    from . import backend
+
+    def cd(a, b):
+        nb, m = b.shape[0], b.shape[1]
+        out = a.new_empty((a.shape[0], nb))
+        d1 = a.new_empty((nb, a.shape[1])); d2 = a.new_empty((nb, m))
+        i1 = torch.empty((nb, a.shape[1]), dtype=torch.int32, device=a.device)
+        i2 = torch.empty((nb, m), dtype=torch.int32, device=a.device)
+        for i in range(a.shape[0]):
+            if backend.chamfer.forward(a[i:i + 1].expand(nb, -1, -1).contiguous(), b, d1, d2, i1, i2) != 1:
+                raise RuntimeError("chamfer_3D.forward failed")
+            out[i] = d1.mean(1) + d2.mean(1)
+        return out
+
+    def emd(a, b):
+        nb = b.shape[0]
+        out = a.new_empty((a.shape[0], nb))
+        for i in range(a.shape[0]):
+            x = a[i:i + 1].expand(nb, -1, -1).contiguous()
+            out[i] = backend.emd.matchcost_forward(x, b, backend.emd.approxmatch_forward(x, b)) / a.shape[1]  # emd.py:48-50
+        return out
+
+    return {"cd": cd, "emd": emd}[metric]
+
+
 def _default_pair_fn(metric):
     from . import backend  # imported lazily: CPU-only tests inject their own pair function
-    return {"cd": backend.chamfer3d_allpairs, "emd": backend.emd_allpairs}[metric]
+    fast = {"cd": backend.chamfer3d_allpairs, "emd": backend.emd_allpairs}[metric]
+    slow = _batched_pairs(metric)
+
+    def fn(a, b):
+        n, m = a.shape[1], b.shape[1]
+        fits = m <= 8192 if metric == "cd" else 20 * n + 24 * m <= 220 * 1024   # chamfer.cu kApMaxM / emd.cu shared memory
+        return fast(a, b) if fits else slow(a.contiguous(), b.contiguous())
+
+    return fn
 
 
 def pairwise_matrix(a, b, metric="cd", pair_fn=None, block=256):
@@ -76,6 +113,31 @@ def pairwise_matrix_sharded(a, b, metric="cd", pair_fn=None, group=None, block=2
     return all_gather_clouds(local, counts, group)
 
 
+def symmetric_matrix_sharded(a, metric="cd", pair_fn=None, group=None, block=256):
+    """[n, n] matrix of a set against itself when the metric is symmetric (Chamfer: dist1.mean() + dist2.mean() with
+    the roles swapped is the same two terms): only the blocks on and above the diagonal are computed — half the pairs
+    — and mirrored.  The upper-triangle blocks are dealt to the ranks round-robin by descending size; one all-reduce
+    (every entry is written by exactly one rank, the others add zero) leaves the full matrix on every rank."""
+    rank, world = _world(group)
+    fn = pair_fn or _default_pair_fn(metric)
+    n = a.shape[0]
+    out = a.new_zeros((n, n))
+    starts = list(range(0, n, block))
+    jobs = [(i, j) for i in starts for j in starts if j >= i]
+    jobs.sort(key=lambda ij: -(min(block, n - ij[0]) * min(block, n - ij[1])))
+    for k, (i, j) in enumerate(jobs):
+        if k % world != rank:
+            continue
+        blk = fn(a[i:i + block].contiguous(), a[j:j + block].contiguous())
+        out[i:i + block, j:j + block] = blk
+        if j != i:
+            out[j:j + block, i:i + block] = blk.t()
+    if world > 1:
+        dist.all_reduce(out, group=group)
+    # the diagonal blocks were computed in full: make them exactly symmetric too (upper triangle wins)
+    return torch.triu(out) + torch.triu(out, 1).t()
+
+
 def mmd_cov(m_sr):
     """PointFlow convention on a [n_sample, n_ref] distance matrix.
     MMD = mean over references of the distance to the closest sample; COV = fraction of references that are the
@@ -98,14 +160,21 @@ def one_nna(m_ss, m_sr, m_rr):
     return {"1nna": float((pred == label).float().mean())}
 
 
-def compute_metrics(samples, refs, metrics=("cd", "emd"), pair_fn=None, group=None, block=256):
-    """samples [ns,N,3], refs [nr,M,3] replicated on every rank -> {"cd": {...}, "emd": {...}}."""
+def compute_metrics(samples, refs, metrics=("cd", "emd"), pair_fn=None, group=None, block=256, symmetric=("cd",)):
+    """samples [ns,N,3], refs [nr,M,3] replicated on every rank -> {"cd": {...}, "emd": {...}}.
+    The S x S and R x R blocks of the 1-NNA test are computed as symmetric matrices (half the pairs) for the metrics
+    named in `symmetric` — Chamfer by default; the auction EMD of (a, b) and (b, a) agree only approximately, so it is
+    evaluated in full unless asked otherwise."""
     out = {}
     for metric in metrics:
         fn = (pair_fn or {}).get(metric) if isinstance(pair_fn, dict) else pair_fn
         m_sr = pairwise_matrix_sharded(samples, refs, metric, fn, group, block)
-        m_ss = pairwise_matrix_sharded(samples, samples, metric, fn, group, block)
-        m_rr = pairwise_matrix_sharded(refs, refs, metric, fn, group, block)
+        if metric in symmetric:
+            m_ss = symmetric_matrix_sharded(samples, metric, fn, group, block)
+            m_rr = symmetric_matrix_sharded(refs, metric, fn, group, block)
+        else:
+            m_ss = pairwise_matrix_sharded(samples, samples, metric, fn, group, block)
+            m_rr = pairwise_matrix_sharded(refs, refs, metric, fn, group, block)
         res = mmd_cov(m_sr)
         res.update(one_nna(m_ss, m_sr, m_rr))
         out[metric] = res

@@ -24,9 +24,10 @@ class AvgVoxelization(Function):
         feats = features.contiguous()
         vox = coords.int().contiguous()
         r = int(resolution)
-        # float_coords (extension, what pcfm.nn.Voxelization passes): where the block will devoxelize; when a backward
-        # pass will follow, its trilinear cell plan is built by the same kernel as the plan of this call
-        fc = float_coords if (float_coords is not None and ctx.needs_input_grad[0]) else None
+        # float_coords (extension, what pcfm.nn.Voxelization passes): where the block will devoxelize; the trilinear
+        # cell plan of those coordinates — used by the devoxelize forward and, in training, by its backward — is built
+        # by the same kernel as the plan of this call
+        fc = float_coords
         out, ind, cnt = _backend.avg_voxelize_forward(feats, vox, r, fc)
         ctx.save_for_backward(ind, cnt)
         return out.view(feats.shape[0], feats.shape[1], r, r, r)

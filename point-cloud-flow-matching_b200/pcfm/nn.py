@@ -35,9 +35,13 @@ class _VoxelCoordCache(threading.local):
         capture = 0
         if coords.is_cuda:
             capture = _lib.stream_capture_id(torch.cuda.current_stream(coords.device).cuda_stream)
-        if (self.ref is None or self.ref() is not coords or coords._version != self.version
+        try:
+            version = coords._version
+        except RuntimeError:   # inference tensors track no version counter: nothing can be memoised on them
+            return _VoxelCoordCache()
+        if (self.ref is None or self.ref() is not coords or version != self.version
                 or capture != self.capture):
-            self.ref, self.version, self.capture = weakref.ref(coords), coords._version, capture
+            self.ref, self.version, self.capture = weakref.ref(coords), version, capture
             self.centred, self.maxnorm, self.by_cfg = None, None, {}
         return self
 

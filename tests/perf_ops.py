@@ -107,7 +107,10 @@ def main():
             be.plan_memo.enabled = False
             ops["vox_fwd_planned"] = planned(ops["vox_fwd"])
             ops["devox_bwd_planned"] = planned(ops["devox_bwd"])
+            ops["devox_fwd_planned"] = planned(ops["devox_fwd"])
+            ops["devox_fwd_eval_planned"] = planned(ops["devox_fwd_eval"])
             byt["vox_fwd_planned"], byt["devox_bwd_planned"] = byt["vox_fwd"], byt["devox_bwd"]
+            byt["devox_fwd_planned"] = byt["devox_fwd"]
         if args.ops:
             ops = {k: v for k, v in ops.items() if k in args.ops.split(",")}
         for op, fn in ops.items():

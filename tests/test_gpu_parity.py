@@ -188,16 +188,33 @@ def test_trilinear_devoxelize(be, oracle, ref, kw):
     e_outs, e_inds, e_wgts = be.pvcnn.trilinear_devoxelize_forward(res, False, cu(coords), cu(vox))
     assert tuple(e_inds.shape) == (1,) and tuple(e_wgts.shape) == (1,)     # trilinear_devox.cpp:45-49
     assert_equal(host(e_outs), host(outs), "eval-mode outs")
-    if kw["c"] % 32 == 0 and res <= 10:   # optional channel-lane kernel (devox.cu): 1 = up to r = 8, 2 = up to r = 10
-        for opt in (1, 2):
-            _lib.set_option("devox_cl", opt)
-            try:
-                p_outs, p_inds, p_wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(coords), cu(vox))
-            finally:
-                _lib.set_option("devox_cl", 0)
-            assert_equal(host(p_inds), o_inds, f"inds (devox_cl={opt})")
-            assert_equal(host(p_wgts), o_wgts, f"wgts (devox_cl={opt})")
-            assert_equal(host(p_outs), host(outs), f"outs (devox_cl={opt}): same FMA order in every forward kernel")
+    # the plane-staging point-lane kernels (the forward without a cell plan: devox_fwd=1, and what few-channel calls
+    # use anyway) and the optional channel-lane kernel (devox_cl: 1 = up to r = 8, 2 = up to r = 10)
+    _lib.set_option("devox_fwd", 1)
+    try:
+        q_outs, q_inds, q_wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(coords), cu(vox))
+        assert_equal(host(q_inds), o_inds, "inds (plane-staging kernels)")
+        assert_equal(host(q_wgts), o_wgts, "wgts (plane-staging kernels)")
+        assert_close(host(q_outs), o_outs, "outs (plane-staging kernels)")
+        assert_close(host(q_outs), host(outs), "outs: cell walk vs plane-staging kernels")
+        if kw["c"] % 32 == 0 and res <= 10:
+            for opt in (1, 2):
+                _lib.set_option("devox_cl", opt)
+                try:
+                    p_outs, p_inds, p_wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cu(coords), cu(vox))
+                finally:
+                    _lib.set_option("devox_cl", 0)
+                assert_equal(host(p_inds), o_inds, f"inds (devox_cl={opt})")
+                assert_equal(host(p_wgts), o_wgts, f"wgts (devox_cl={opt})")
+                assert_equal(host(p_outs), host(q_outs), f"outs (devox_cl={opt}): same FMA order in the point / channel-lane kernels")
+    finally:
+        _lib.set_option("devox_fwd", 0)
+    # a second call on the SAME coords tensor reuses the memoised plan (pcfm_trilinear_devoxelize_forward_cells, planned)
+    cc, vv = cu(coords), cu(vox)
+    first = be.pvcnn.trilinear_devoxelize_forward(res, True, cc, vv)
+    again = be.pvcnn.trilinear_devoxelize_forward(res, True, cc, vv)
+    assert_equal(host(again[0]), host(first[0]), "outs on the reused plan")
+    assert_equal(host(again[1]), o_inds, "inds on the reused plan")
     o_gx = oracle.trilinear_devoxelize_backward(gy, o_inds, o_wgts, res)
     for variant in (0, 1):
         _lib.set_option("devox_bwd", variant)

@@ -57,7 +57,10 @@ def _worker(rank, world, port, out_dir):
         full = ev.pairwise_matrix_sharded(S, R_full, "cd", pair_fn=tc.chamfer_allpairs, block=2)
         lo2, hi2, local = ev.pairwise_matrix_sharded(S, R_full, "cd", pair_fn=tc.chamfer_allpairs, block=3, gather=False)
         res = ev.compute_metrics(S, R_full, metrics=("cd",), pair_fn=tc.chamfer_allpairs, block=4)
-        torch.save({"full": full, "lo": lo2, "hi": hi2, "local": local, "res": res}, os.path.join(out_dir, f"r{rank}.pt"))
+        res_full = ev.compute_metrics(S, R_full, metrics=("cd",), pair_fn=tc.chamfer_allpairs, block=4, symmetric=())
+        sym = ev.symmetric_matrix_sharded(S, "cd", pair_fn=tc.chamfer_allpairs, block=3)   # 3 + 3 + 1 rows: 6 blocks
+        torch.save({"full": full, "lo": lo2, "hi": hi2, "local": local, "res": res, "res_full": res_full, "sym": sym},
+                   os.path.join(out_dir, f"r{rank}.pt"))
         dist.barrier()
     finally:
         dist.destroy_process_group()
@@ -76,6 +79,13 @@ def test_sharded_allpairs_world2_matches_single_process(tmp_path):
         assert (o["lo"], o["hi"]) == ev.shard_range(7, r, world)
         assert torch.allclose(o["local"], want[o["lo"]:o["hi"]], rtol=1e-6, atol=1e-7)
     assert outs[0]["res"] == outs[1]["res"]
+    # S x S computed as a symmetric matrix (upper-triangle blocks dealt to the ranks, one all-reduce, mirrored)
+    want_ss = tc.chamfer_allpairs(S, S)
+    for r, o in enumerate(outs):
+        assert torch.equal(o["sym"], o["sym"].t()), f"rank {r}: not symmetric"
+        assert torch.allclose(o["sym"], want_ss, rtol=1e-6, atol=1e-7), f"rank {r} symmetric matrix"
+        for k, v in o["res_full"]["cd"].items():   # half the pairs, same metrics
+            assert abs(v - o["res"]["cd"][k]) < 1e-6
     single = ev.compute_metrics(S, R, metrics=("cd",), pair_fn=tc.chamfer_allpairs, block=4)
     for k, v in single["cd"].items():
         assert abs(v - outs[0]["res"]["cd"][k]) < 1e-6
