@@ -214,6 +214,15 @@ int pcfm_three_nn_interpolate_backward(const float* grad_y, const int* idx, cons
  * Distances are evaluated exactly as the reference SASS: d = fma(dz,dz,fma(dx,dx,dy*dy)) on (other - self). */
 int pcfm_chamfer3d_forward(const float* xyz1, const float* xyz2, int b, int n, int m,
                            float* dist1, float* dist2, int* idx1, int* idx2, pcfm_stream_t stream);
+/* Same outputs, bit for bit (distances, and arg-min indices including the lowest-index tie rule), with every squared
+ * distance evaluated ONCE for both directions: row minima in registers, column minima combined through 64-bit
+ * (distance bits << 32 | index) atomicMin keys in `workspace` (pcfm_chamfer3d_forward_workspace bytes).  This is the
+ * entry pcfm.backend.chamfer.forward uses; the entry above (two directional passes, no workspace) is kept for callers
+ * without scratch memory. */
+size_t pcfm_chamfer3d_forward_workspace(int b, int n, int m);
+int pcfm_chamfer3d_forward_ws(const float* xyz1, const float* xyz2, int b, int n, int m,
+                              float* dist1, float* dist2, int* idx1, int* idx2,
+                              void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
 /* chamfer_3D.backward (chamfer_cuda.cpp:22-26): ACCUMULATES into gradxyz1 f32[B,N,3], gradxyz2 f32[B,M,3]
  * (caller zeroes them, as dist_chamfer_3D.py:75-79 does). */
 int pcfm_chamfer3d_backward(const float* xyz1, const float* xyz2, const float* graddist1, const float* graddist2,

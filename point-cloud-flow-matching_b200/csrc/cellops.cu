@@ -63,6 +63,8 @@ __global__ void __launch_bounds__(kVoxThreads, 2)
   }
   griddep_wait();   // everything above is independent of the plan (PDL: overlaps the plan kernel)
   griddep_launch_dependents();  // chained PDL: the next kernel on the stream may be scheduled behind this one
+  cells = after_wait(cells); slot0 = after_wait(slot0); meta = after_wait(meta); heavy = after_wait(heavy);
+  rec = after_wait(rec);
   __syncthreads();  // row visible; zero stores ordered before the sums below (same CTA)
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
@@ -136,7 +138,7 @@ __global__ void __launch_bounds__(kVoxThreads, 2)
         else atomicAdd(o + t, acc);   // a piece of a split cell: the row was zeroed above (same CTA, before the barrier)
       }
     }
-    cur = nxt;
+    cur = take_cell_item(nxt);
   }
 }
 

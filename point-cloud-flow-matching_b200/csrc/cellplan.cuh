@@ -71,16 +71,27 @@ __device__ __forceinline__ CellItem next_cell_item(int* counter, int nslice, int
   const int lane = threadIdx.x & 31;
   CellItem c;
   c.item = 0;
-  if (lane == 0) c.item = atomicAdd(counter, 1);
+  // one shared-memory atomic per warp (written in PTX: the compiler wraps a C++ atomicAdd under `if (lane == 0)` in
+  // its warp-aggregation sequence, ~15 instructions per item)
+  if (lane == 0)
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(c.item) : "r"(smem_u32(counter)) : "memory");
   c.item = __shfl_sync(0xffffffffu, c.item, 0);
   c.h = make_int4(0, 0, 0, 0);
   if (c.item < nslice) {
-    c.h.x = cl[(c.item << 5) | lane];
-    c.h.y = sl[(c.item << 5) | lane];
+    c.h.x = __ldg(cl + ((c.item << 5) | lane));
+    c.h.y = __ldg(sl + ((c.item << 5) | lane));
   } else if (c.item < nitem) {
-    c.h = hv[c.item - nslice];
+    c.h = __ldg(hv + (c.item - nslice));
   }
   return c;
+}
+// Makes a prefetched item the current one.  The empty asm pins the header registers to THIS point of the program:
+// without it the compiler moves the warp-uniform fields of a heavy header into uniform registers (R2UR) right behind
+// the load, i.e. it waits for the L2 round trip one item early and the prefetch hides nothing (ncu: 500 stall samples
+// on that R2UR).
+__device__ __forceinline__ CellItem take_cell_item(CellItem n) {
+  asm volatile("" : "+r"(n.item), "+r"(n.h.x), "+r"(n.h.y), "+r"(n.h.z), "+r"(n.h.w));
+  return n;
 }
 
 // packed fp32 pairs (sm_100: FADD2 / FMUL2 / FFMA2, every lane rounded like the scalar instruction)

@@ -115,6 +115,168 @@ __global__ void __launch_bounds__(kChThreads)
   }
 }
 
+
+// =================================================================================================
+// Single-pass operator: every squared distance is evaluated ONCE and feeds both directions (the reference and the
+// kernel above evaluate it twice, once per direction: chamfer3D.cu:136-154 launches NmDistanceKernel twice).
+//
+// Tile = RA*128 rows of xyz1 (thread t owns the RA CONTIGUOUS rows t*RA .. t*RA+RA-1, in registers) x a range of
+// columns of xyz2 (streamed through shared memory).  Row side: running minimum per row over groups of four columns
+// (strict <: the first group that reaches the minimum wins, resolved to the lowest column at the end), exactly as
+// chamfer_nn_kernel.  Column side: per column the minimum over a thread's rows is folded on the IEEE bit patterns
+// (distances are >= +0, where unsigned order == float order; VIMNMX3 folds two rows per instruction), reduced over
+// the warp with REDUX.MIN, and the LOWEST lane that holds the minimum is elected: because a thread's rows are
+// contiguous and threads are numbered in row order, the lowest thread that attains the minimum contains the lowest
+// row that attains it.  Results of different tiles meet in 64-bit keys  (bits(d) << 32) | index  combined with
+// atomicMin: smallest distance first, lowest index on ties — the reference's tie rule (chamfer3D.cu:36,126) without any
+// ordering between tiles.  A small kernel unpacks the keys and resolves the winning thread of a column to its row.
+// Issue slots per distance: 3 (packed arithmetic) + ~1 (row minimum) + 0.5 (column minimum), against ~4.5 per
+// direction before.
+// =================================================================================================
+constexpr int kOnceThreads = 128;
+
+template <int RA>
+__global__ void __launch_bounds__(kOnceThreads)
+    chamfer_once_kernel(const float* __restrict__ a, const float* __restrict__ o, int n, int m, int cols_per_tile,
+                        unsigned long long* __restrict__ rowkey, unsigned long long* __restrict__ colkey) {
+  __shared__ __align__(16) float bx[kChChunk], by[kChChunk], bz[kChChunk];
+  const int b = blockIdx.z;
+  const float* ab = a + (long long)b * n * 3;
+  const float* ob = o + (long long)b * m * 3;
+  unsigned long long* rk = rowkey + (long long)b * n;
+  unsigned long long* ck = colkey + (long long)b * m;
+  const int gti = blockIdx.x * kOnceThreads + threadIdx.x;   // thread index in row order: rows gti*RA .. gti*RA+RA-1
+  const int lane = threadIdx.x & 31;
+  float ax[RA], ay[RA], az[RA], best[RA];
+  unsigned long long axp[RA], ayp[RA], azp[RA];
+  int bk[RA];
+#pragma unroll
+  for (int r = 0; r < RA; ++r) {
+    const int i = gti * RA + r;
+    const bool v = i < n;   // rows past the end sit at +inf: their distances never lower a minimum
+    ax[r] = v ? ab[(long long)i * 3 + 0] : pos_inf();
+    ay[r] = v ? ab[(long long)i * 3 + 1] : pos_inf();
+    az[r] = v ? ab[(long long)i * 3 + 2] : pos_inf();
+    axp[r] = pack2(ax[r], ax[r]);
+    ayp[r] = pack2(ay[r], ay[r]);
+    azp[r] = pack2(az[r], az[r]);
+    best[r] = pos_inf();
+    bk[r] = 0;
+  }
+  const int c_lo = blockIdx.y * cols_per_tile, c_hi = min(m, c_lo + cols_per_tile);
+  for (int k2 = c_lo; k2 < c_hi; k2 += kChChunk) {
+    const int len = min(kChChunk, c_hi - k2);
+    const int len4 = (len + 3) & ~3;
+    __syncthreads();
+    for (int k = threadIdx.x; k < len4; k += kOnceThreads) {
+      const bool v = k < len;  // padding: distance +inf, never a strict minimum
+      const float* p = ob + (long long)(k2 + (v ? k : 0)) * 3;
+      bx[k] = v ? p[0] : pos_inf();
+      by[k] = v ? p[1] : pos_inf();
+      bz[k] = v ? p[2] : pos_inf();
+    }
+    __syncthreads();
+    for (int k = 0; k < len4; k += 4) {
+      const ulonglong2 qx = *reinterpret_cast<const ulonglong2*>(bx + k);  // (x0,x1) (x2,x3)
+      const ulonglong2 qy = *reinterpret_cast<const ulonglong2*>(by + k);
+      const ulonglong2 qz = *reinterpret_cast<const ulonglong2*>(bz + k);
+      unsigned cm0 = 0x7f800000u, cm1 = 0x7f800000u, cm2 = 0x7f800000u, cm3 = 0x7f800000u;
+#pragma unroll
+      for (int r = 0; r < RA; r += 2) {
+        unsigned u0, u1, u2, u3, w0, w1, w2, w3;
+        sq3x2(sub2(qx.x, axp[r]), sub2(qy.x, ayp[r]), sub2(qz.x, azp[r]), u0, u1);
+        sq3x2(sub2(qx.y, axp[r]), sub2(qy.y, ayp[r]), sub2(qz.y, azp[r]), u2, u3);
+        sq3x2(sub2(qx.x, axp[r + 1]), sub2(qy.x, ayp[r + 1]), sub2(qz.x, azp[r + 1]), w0, w1);
+        sq3x2(sub2(qx.y, axp[r + 1]), sub2(qy.y, ayp[r + 1]), sub2(qz.y, azp[r + 1]), w2, w3);
+        const float m4u = fminf(fminf(__uint_as_float(u0), __uint_as_float(u1)),
+                                fminf(__uint_as_float(u2), __uint_as_float(u3)));
+        const float m4w = fminf(fminf(__uint_as_float(w0), __uint_as_float(w1)),
+                                fminf(__uint_as_float(w2), __uint_as_float(w3)));
+        if (m4u < best[r]) {  // strict: the first group of four that reaches the minimum wins
+          best[r] = m4u;
+          bk[r] = k2 + k;
+        }
+        if (m4w < best[r + 1]) {
+          best[r + 1] = m4w;
+          bk[r + 1] = k2 + k;
+        }
+        cm0 = __vimin3_u32(cm0, u0, w0);
+        cm1 = __vimin3_u32(cm1, u1, w1);
+        cm2 = __vimin3_u32(cm2, u2, w2);
+        cm3 = __vimin3_u32(cm3, u3, w3);
+      }
+      // column side: warp minimum, lowest lane that holds it, one 64-bit atomicMin per column and warp (skipped when
+      // the key in memory is already smaller)
+      const unsigned cmv[4] = {cm0, cm1, cm2, cm3};
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const unsigned wm = __reduce_min_sync(0xffffffffu, cmv[t]);
+        const unsigned who = __ballot_sync(0xffffffffu, cmv[t] == wm);
+        const int col = k2 + k + t;
+        if (lane == 0 && col < c_hi && wm < 0x7f800000u) {
+          const unsigned long long key = ((unsigned long long)wm << 32) | (unsigned)(gti + (__ffs(who) - 1));
+          if (key < *(volatile unsigned long long*)(ck + col)) atomicMin(ck + col, key);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < RA; ++r) {
+    const int i = gti * RA + r;
+    if (i >= n) continue;
+    // lowest index inside the winning group of four: recompute the (bit-identical) distances
+    int bi = bk[r];
+    for (int t = 0; t < 4; ++t) {
+      const int k = bk[r] + t;
+      if (k >= c_hi) break;
+      const float* p = ob + (long long)k * 3;
+      const float d = sq3(p[0] - ax[r], p[1] - ay[r], p[2] - az[r]);
+      if (d == best[r]) {
+        bi = k;
+        break;
+      }
+    }
+    const unsigned long long key = ((unsigned long long)__float_as_uint(best[r]) << 32) | (unsigned)bi;
+    if (gridDim.y == 1) rk[i] = key;
+    else atomicMin(rk + i, key);
+  }
+}
+
+// keys -> (dist, idx); a column's key names the winning THREAD of chamfer_once_kernel: its lowest row at that distance
+__global__ void __launch_bounds__(256)
+    chamfer_once_finish_kernel(const float* __restrict__ a, const float* __restrict__ o, int n, int m, int ra,
+                               const unsigned long long* __restrict__ rowkey,
+                               const unsigned long long* __restrict__ colkey, float* __restrict__ dist1,
+                               int* __restrict__ idx1, float* __restrict__ dist2, int* __restrict__ idx2) {
+  const int b = blockIdx.y;
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) {
+    const unsigned long long key = rowkey[(long long)b * n + j];
+    dist1[(long long)b * n + j] = __uint_as_float((unsigned)(key >> 32));
+    idx1[(long long)b * n + j] = (int)(unsigned)key;
+  }
+  if (j < m) {
+    const unsigned long long key = colkey[(long long)b * m + j];
+    const unsigned bits = (unsigned)(key >> 32);
+    const float* p = o + ((long long)b * m + j) * 3;
+    const float x = p[0], y = p[1], z = p[2];
+    const int r0 = (int)(unsigned)key * ra;
+    int bi = r0;
+    for (int t = 0; t < ra; ++t) {
+      const int i = r0 + t;
+      if (i >= n) break;
+      const float* q = a + ((long long)b * n + i) * 3;
+      // same operand order as the row side of the kernel above (column - row): bit-identical
+      if (__float_as_uint(sq3(x - q[0], y - q[1], z - q[2])) == bits) {
+        bi = i;
+        break;
+      }
+    }
+    dist2[(long long)b * m + j] = __uint_as_float(bits);
+    idx2[(long long)b * m + j] = bi;
+  }
+}
+
 // gradient (chamfer3D.cu:155-174, both launches fused): accumulates into grad1 / grad2
 __global__ void __launch_bounds__(256)
     chamfer_grad_kernel(const float* __restrict__ xyz1, const float* __restrict__ xyz2,
@@ -301,6 +463,45 @@ int pcfm_chamfer3d_forward(const float* xyz1, const float* xyz2, int b, int n, i
     }
     PCFM_LAUNCHED();
   }
+  return 0;
+}
+
+
+size_t pcfm_chamfer3d_forward_workspace(int b, int n, int m) {
+  if (b <= 0 || n <= 0 || m <= 0) return 256;
+  return align256((size_t)b * n * 8) + align256((size_t)b * m * 8) + 256;
+}
+
+int pcfm_chamfer3d_forward_ws(const float* xyz1, const float* xyz2, int b, int n, int m, float* dist1, float* dist2,
+                              int* idx1, int* idx2, void* workspace, size_t workspace_bytes, pcfm_stream_t stream) {
+  if (b < 0 || n < 0 || m < 0) return PCFM_E_BADARG;
+  if (b == 0 || n == 0 || m == 0) return 0;  // the reference's loops do not execute: outputs untouched
+  if (!xyz1 || !xyz2 || !dist1 || !dist2 || !idx1 || !idx2) return PCFM_E_BADARG;
+  if (b > 65535) return pcfm_chamfer3d_forward(xyz1, xyz2, b, n, m, dist1, dist2, idx1, idx2, stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  Workspace ws(workspace, workspace_bytes);
+  unsigned long long* rowkey = ws.take<unsigned long long>((size_t)b * n);
+  unsigned long long* colkey = ws.take<unsigned long long>((size_t)b * m);
+  if (!ws.ok()) return PCFM_E_WORKSPACE;
+  // rows per thread: as many as keep the grid at >= 2 CTAs per SM together with the column split below
+  const long long want = 2LL * num_sms();
+  int ra = 16;
+  while (ra > 4 && (long long)cdiv(n, kOnceThreads * ra) * b * cdiv(m, kChChunk) < want) ra >>= 1;
+  const int rowtiles = cdiv(n, kOnceThreads * ra);
+  int coltiles = (int)((want + (long long)rowtiles * b - 1) / ((long long)rowtiles * b));
+  coltiles = max(1, min(coltiles, cdiv(m, kChChunk)));
+  const int cols_per_tile = cdiv(cdiv(m, coltiles), 4) * 4;
+  coltiles = cdiv(m, cols_per_tile);
+  PCFM_CUDA(cudaMemsetAsync(colkey, 0xff, (size_t)b * m * 8, st));
+  if (coltiles > 1) PCFM_CUDA(cudaMemsetAsync(rowkey, 0xff, (size_t)b * n * 8, st));
+  dim3 grid(rowtiles, coltiles, b);
+  if (ra == 16) chamfer_once_kernel<16><<<grid, kOnceThreads, 0, st>>>(xyz1, xyz2, n, m, cols_per_tile, rowkey, colkey);
+  else if (ra == 8) chamfer_once_kernel<8><<<grid, kOnceThreads, 0, st>>>(xyz1, xyz2, n, m, cols_per_tile, rowkey, colkey);
+  else chamfer_once_kernel<4><<<grid, kOnceThreads, 0, st>>>(xyz1, xyz2, n, m, cols_per_tile, rowkey, colkey);
+  PCFM_LAUNCHED();
+  dim3 g2(cdiv(n > m ? n : m, 256), b);
+  chamfer_once_finish_kernel<<<g2, 256, 0, st>>>(xyz1, xyz2, n, m, ra, rowkey, colkey, dist1, idx1, dist2, idx2);
+  PCFM_LAUNCHED();
   return 0;
 }
 

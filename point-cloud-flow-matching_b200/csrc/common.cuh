@@ -30,6 +30,11 @@ extern int g_opt_fps;           // 0 = cluster FPS (points in registers) when th
 extern int g_opt_gather_bwd;    // 0 = gather backward with atomics (like the reference), 1 = sorted-segment sums
 extern int g_opt_devox_fwd;     // 0 = devoxelize forward as a walk over the trilinear cell plan when the caller offers a
                                 // workspace (default), 1 = always the plane-staging point-lane kernels
+extern int g_opt_tri2;          // two-channel persistent trilinear walks (tri2.cu): 0 = off (default: measured slower, see
+                                // tri2.cu), 1 = forward and backward, 2 = forward only, 3 = backward only
+extern int g_opt_bwd_phases;    // devoxelize backward, light cells: 0 = shared-memory atomics (default), 1 = static rounds +
+                                // 8 conflict-free corner phases (deterministic order; measured 0-15 % slower: barrier stalls)
+extern int g_opt_dbg;           // measurement only (tri2 forward): 1 skip light slices, 2 skip heavy pieces, 4 no row stores
 extern int g_opt_plan;          // 0 = fused cell-plan build when it fits, 1 = always the multi-kernel build
 extern int g_num_sms;           // cached SM count of the current device (148 on B200)
 int num_sms();
@@ -189,6 +194,16 @@ __device__ __forceinline__ void stage_floats(float* smem_dst, const float* gmem_
 // and its memory is visible).  Both are no-ops for kernels launched normally.
 __device__ __forceinline__ void griddep_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+// Pointers to data the PREVIOUS grid writes (the cell plan) must be passed through this after griddep_wait(): loads
+// through `const __restrict__` pointers are invariant loads (ld.global.nc) which the compiler may hoist above the wait —
+// observed: the plan's `meta` load of a persistent kernel's first job moved in front of the wait and read the plan of
+// the previous call.  The empty asm makes the pointer value (and so every load through it) depend on this program point.
+template <typename T>
+__device__ __forceinline__ const T* after_wait(const T* p) {
+  asm volatile("" : "+l"(p) : : "memory");
+  return p;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -14,6 +14,9 @@ int g_opt_vox_fwd = 0;
 int g_opt_stage = 0;
 int g_opt_plan = 0;
 int g_opt_devox_fwd = 0;
+int g_opt_tri2 = 0;
+int g_opt_bwd_phases = 0;
+int g_opt_dbg = 0;
 int g_opt_gather_bwd = 0;
 int g_opt_fps = 0;
 int g_opt_pdl = 2;
@@ -80,6 +83,10 @@ int pcfm_set_option(const char* key, int value) {
   if (!strcmp(key, "gather_bwd")) { pcfm::g_opt_gather_bwd = value; return 0; }
   if (!strcmp(key, "plan")) { pcfm::g_opt_plan = value; return 0; }
   if (!strcmp(key, "devox_fwd")) { pcfm::g_opt_devox_fwd = value; return 0; }
+  if (!strcmp(key, "tri2")) { pcfm::g_opt_tri2 = value; return 0; }
+  if (!strcmp(key, "dbg")) { pcfm::g_opt_dbg = value; return 0; }
+  if (!strcmp(key, "bwd_phases")) { pcfm::g_opt_bwd_phases = value; return 0; }
+  if (!strcmp(key, "chamfer_once")) return 0;  // host-side choice (pcfm/backend.py): 1 = pcfm_chamfer3d_forward_ws [default]
   return PCFM_E_BADARG;
 }
 

@@ -12,6 +12,13 @@
 
 namespace pcfm {
 
+// tri2.cu: two channels per CTA, persistent
+bool tri2_fwd_ok(int c, int n, int r);
+bool tri2_bwd_ok(int c, int n, int r);
+int launch_tri2_fwd(const float* vox, const CellPlan& plan, float* outs, int b, int c, int n, int r, cudaStream_t st);
+int launch_tri2_bwd(const float* grad_y, const CellPlan& plan, float* grad_x, int b, int c, int n, int r, bool reused,
+                    cudaStream_t st);
+
 constexpr size_t kTriSmemLimit = 227 * 1024 - 512;  // opt-in maximum (232448 B) minus the static shared memory
 
 // ---- the two points of a pair slot -------------------------------------------------------------------------------
@@ -64,12 +71,11 @@ __device__ __forceinline__ f32x2_t tri_fwd_interpolate(const TriPair& t, const f
 // Walks pair slots first, first + step, ... < end of one cell (or of one lane's share of a heavy piece), two slots per
 // round (j and j + second), and hands every pair to `body`.  Slot j sits at pa[j * mul] / pb[j * mul] (light cell of a
 // sliced-ELL slice: mul = 32, second = 1, step = 2; lane of a heavy piece: mul = 1, second = 32, step = 64, first = lane).
-// PIPE: the loads of round i+1 are issued before round i is processed, so one round of L2 latency is always hidden
-// behind the arithmetic (the walk is latency-bound: a round is 4 dependent 16-byte loads per lane).  A missing second
-// slot is replaced by a dummy pair (offsets 4*N, zero fractions): it gathers the exact zero behind the row / stores to
+// PIPE (off: measured 5-10 % slower, the register rotation costs ~20 moves per round and the kernels are issue-bound):
+// the loads of round i+1 are issued before round i is processed.  A missing second slot is replaced by a dummy pair (offsets 4*N, zero fractions): it gathers the exact zero behind the row / stores to
 // the scratch slot behind it.
 #ifndef PCFM_TRI_PIPE
-#define PCFM_TRI_PIPE 1
+#define PCFM_TRI_PIPE 0
 #endif
 template <typename Body>
 __device__ __forceinline__ void tri_walk(const float4* __restrict__ pa, const float4* __restrict__ pb, int first, int end,
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(1024, 1)
     tri_bwd_kernel(const float* __restrict__ grad_y, const int* __restrict__ cells, const int* __restrict__ slot0,
                    const int* __restrict__ meta, const int* __restrict__ heavy, const float4* __restrict__ recA,
                    const float4* __restrict__ recB, float* __restrict__ grad_x, int C, int N, int r, int lcap,
-                   int hcap, int rcap, int use_tma, int wait_first) {
+                   int hcap, int rcap, int use_tma, int wait_first, int phases) {
   extern __shared__ __align__(128) float smem[];
   __shared__ uint64_t bar;
   __shared__ int next_item;
@@ -160,6 +166,8 @@ __global__ void __launch_bounds__(1024, 1)
   }
   griddep_wait();  // everything above is independent of the plan (PDL: overlaps the plan kernel)
   griddep_launch_dependents();  // chained PDL: the next kernel on the stream may be scheduled behind this one
+  cells = after_wait(cells); slot0 = after_wait(slot0); meta = after_wait(meta); heavy = after_wait(heavy);
+  recA = after_wait(recA); recB = after_wait(recB);
   __syncthreads();
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
@@ -177,11 +185,57 @@ __global__ void __launch_bounds__(1024, 1)
   int off[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) off[k] = (k >> 2) * r2 + ((k >> 1) & 1) * r + (k & 1);
-  // Work items, taken from a shared counter by whole warps:
-  //   [0, nslice)           slices of 32 light cells, longest cells first (count-sorted plan)
-  //   [nslice, nslice + h1) pieces (<= kHeavyChunk records) of heavy cells
   const int nslice = l1 >> 5, nitem = nslice + h1;
   const int4* hv = (const int4*)heavy + (long long)b * hcap;
+  const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5;
+  // ---- light cells (sliced-ELL, one thread per cell): the 8 corner sums of a cell's points are built in registers.
+  // Neighbouring cells share voxels, so adding them to the plane needs care.  A shared-memory float atomicAdd is a CAS
+  // loop whose 32 lanes are served one by one (ncu: ~30 wavefronts per warp instruction, two thirds of all shared-memory
+  // traffic of the kernel).  With `phases` (pcfm_set_option("bwd_phases", 1)) the slices are dealt to the warps in ROUNDS
+  // (slice = round * warps + warp: count-sorted, so the slices of a round are equally long) and after every round the
+  // CTA adds corner 0 of all its cells, then corner 1, ... : cell -> cell + offset(k) is injective, so inside a phase
+  // no two threads touch the same voxel and the add is a plain load / add / store.  8 barriers per round, ~2-4 rounds
+  // per row; a voxel's light contributions then arrive in a fixed order.  Measured (B=8, N=20000): the atomics' wavefronts
+  // are gone but the barriers stall as long (r=32: 0.136 -> 0.135 ms, r=16: 0.130 -> 0.143, r=8: 0.110 -> 0.122), so the
+  // atomic walk below stays the default.
+  const bool phased = PLANE_SMEM && phases != 0;
+  if (phased) {
+    int hx = 0, hy = 0;
+    if (warp < nslice) {
+      hx = __ldg(cl + ((warp << 5) | lane));
+      hy = __ldg(sl + ((warp << 5) | lane));
+    }
+    for (int rd = 0; rd * nw < nslice; ++rd) {
+      const int n = (int)((unsigned)hx >> 24);  // 0 = alignment hole / no slice for this warp in this round
+      const int cell = hx & 0xffffff;
+      const unsigned se = (unsigned)hy;
+      const unsigned mask = n ? se >> 24 : 0u;
+      const int nx_item = (rd + 1) * nw + warp;   // next round's header in flight during this round
+      hx = 0;
+      if (nx_item < nslice) {
+        hx = __ldg(cl + ((nx_item << 5) | lane));
+        hy = __ldg(sl + ((nx_item << 5) | lane));
+      }
+      f32x2_t s[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s[k] = 0ull;
+      tri_walk(ra + (se & 0xffffff), rb + (se & 0xffffff), 0, (n + 1) >> 1, 2, 1, 32, dummy,
+               [&](const TriPair t) { tri_bwd_accumulate(t, gather(t.off0), gather(t.off1), s); });
+      float* pv = plane + cell;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float lo, hi;
+        upk2(s[k], lo, hi);
+        if ((mask >> k) & 1u) pv[off[k]] += lo + hi;
+        __syncthreads();
+      }
+      asm volatile("" : "+r"(hx), "+r"(hy));  // keep the prefetched header in plain registers until here
+    }
+  }
+  // ---- heavy cell pieces (and, for grids beyond shared memory, everything): whole warps take items from a shared
+  // counter; cell sums are added with atomics (8 per piece; global RED.ADD when the plane is not staged) ----
+  if (threadIdx.x == 0) next_item = phased ? nslice : 0;
+  __syncthreads();
   CellItem cur = next_cell_item(&next_item, nslice, nitem, cl, sl, hv);
   while (cur.item < nitem) {
     const CellItem nxt = next_cell_item(&next_item, nslice, nitem, cl, sl, hv);  // header in flight during this item
@@ -189,9 +243,6 @@ __global__ void __launch_bounds__(1024, 1)
 #pragma unroll
     for (int k = 0; k < 8; ++k) s[k] = 0ull;
     if (cur.item < nslice) {
-      // Light cells (sliced-ELL): one thread per cell sums the 8 corner contributions of its points in registers,
-      // then adds them into the plane.  Neighbouring cells share voxels, so the add is a shared-memory atomicAdd
-      // (a CAS loop on sm_100a; collisions need two adjacent cells to finish in the same few cycles).
       const int d = cur.h.x;
       const int n = (int)((unsigned)d >> 24);  // 0 = alignment hole
       const int cell = d & 0xffffff;
@@ -246,7 +297,7 @@ __global__ void __launch_bounds__(1024, 1)
         if ((hd.w >> k) & 1) atomicAdd(plane + cell + (k >> 2) * r2 + ((k >> 1) & 1) * r + (k & 1), a1);
       }
     }
-    cur = nxt;
+    cur = take_cell_item(nxt);
   }
   if (!PLANE_SMEM) return;
   __syncthreads();
@@ -285,6 +336,8 @@ static int devox_bwd_cells(const float* grad_y, const float* coords, int b, int 
   int rc = reused ? cellplan_attach(true, b, n, t, &plan, &ws)
                   : cellplan_build(nullptr, coords, r, nullptr, b, n, t, nullptr, &plan, &ws, st);
   if (rc) return rc;
+  if ((g_opt_tri2 & 1) != 0 && plane_smem && tri2_bwd_ok(c, n, r))
+    return launch_tri2_bwd(grad_y, plan, grad_x, b, c, n, r, reused, st);
   dim3 grid(c, b);
   const bool row_smem = tri_bwd_smem(n, r, true, plane_smem) <= kTriSmemLimit;
   const size_t smem = tri_bwd_smem(n, r, row_smem, plane_smem);
@@ -300,7 +353,7 @@ static int devox_bwd_cells(const float* grad_y, const float* coords, int b, int 
     PCFM_CUDA(launch_dependent(tri_bwd_kernel<RS, PS>, grid, dim3(threads), smem, st, dep, grad_y, plan.cells,   \
                                plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec,                       \
                                (const float4*)plan.rec2, grad_x, c, n, r, plan.lcap, plan.hcap, plan.rcap, tma,  \
-                               (int)reused));                                                                    \
+                               (int)reused, g_opt_bwd_phases));                                                  \
   } while (0)
   if (plane_smem && row_smem) PCFM_DBWD(true, true);
   else if (plane_smem) PCFM_DBWD(false, true);
@@ -314,9 +367,14 @@ static int devox_bwd_cells(const float* grad_y, const float* coords, int b, int 
 // =================================================================================================
 // forward
 // =================================================================================================
-// Shared memory: [output row: N floats][one scratch float: the dummy half of an odd cell].  The voxel plane is read
-// straight from global memory (8 corner loads per cell / per lane of a heavy piece, L1-cached): nothing is staged, so
-// two CTAs of 512 threads share an SM at N = 20000 whatever the grid resolution.
+// Shared memory: [voxel plane: P floats (PLANE_SMEM)][output row: N floats][scratch: the dummy half of an odd cell].
+// The lanes of a light slice own 32 unrelated cells (the plan sorts cells by size): read from global memory their 8
+// corner loads touch 32 different lines each, and ncu showed those loads filling the L1 data pipe (63 % at r = 16).
+// PLANE_SMEM: small planes (r <= 20: <= 32 KB) are staged by one TMA bulk copy and the corners come from shared
+// memory (~3 wavefronts per gather instead of 32); two CTAs of 512 threads still share an SM at N = 20000.  Larger
+// planes are read straight from global memory (L1-cached).
+// RT > 0: the grid resolution at compile time (8 / 16 / 32: the 8 corner offsets become immediates of the loads).
+template <int RT, bool PLANE_SMEM>
 __global__ void __launch_bounds__(512, 2)
     tri_fwd_kernel(const float* __restrict__ vox, const int* __restrict__ cells, const int* __restrict__ slot0,
                    const int* __restrict__ meta, const int* __restrict__ heavy, const float4* __restrict__ recA,
@@ -324,15 +382,28 @@ __global__ void __launch_bounds__(512, 2)
                    int rcap, int use_tma) {
   extern __shared__ __align__(128) float smem[];
   __shared__ int next_item;
+  __shared__ uint64_t bar;
   griddep_wait();  // the plan (and, chained, whatever produced `vox`) is complete
   griddep_launch_dependents();
+  vox = after_wait(vox); cells = after_wait(cells); slot0 = after_wait(slot0); meta = after_wait(meta);
+  heavy = after_wait(heavy); recA = after_wait(recA); recB = after_wait(recB);
+  if (RT > 0) r = RT;
   const int r2 = r * r, P = r2 * r;
   const int c = blockIdx.x, b = blockIdx.y;
-  const float* plane = vox + ((long long)b * C + c) * P;
+  const float* plane_g = vox + ((long long)b * C + c) * P;
   float* o = outs + ((long long)b * C + c) * N;
-  char* rowb = (char*)smem;
-  if (threadIdx.x == 0) next_item = 0;
+  float* row = smem + (PLANE_SMEM ? ((P + 3) & ~3) : 0);
+  char* rowb = (char*)row;
+  if (threadIdx.x == 0) {
+    next_item = 0;
+    if (PLANE_SMEM) {
+      mbar_init(&bar, 1);
+      fence_mbar_init();
+    }
+  }
   __syncthreads();
+  if (PLANE_SMEM) stage_floats(smem, plane_g, P, &bar, 0, use_tma != 0);
+  const float* plane = PLANE_SMEM ? smem : plane_g;
   const int* cl = cells + (long long)b * lcap;
   const int* sl = slot0 + (long long)b * lcap;
   const float4* ra = recA + (long long)b * rcap;
@@ -353,12 +424,22 @@ __global__ void __launch_bounds__(512, 2)
     const int cell = light ? (cur.h.x & 0xffffff) : cur.h.x;
     const unsigned mask = light ? (n ? (unsigned)cur.h.y >> 24 : 0u) : (unsigned)cur.h.w;
     // the cell's 8 corner values: a corner beyond the grid carries weight exactly 0 for every point of the cell
-    // (trilinear_devox.cu:64-75 skips it by not offsetting the index) and is not read
+    // (trilinear_devox.cu:64-75 skips it by not offsetting the index) and is not read.  Interior cells (all of a warp's
+    // cells, nearly always) take 8 plain loads at constant offsets from one base pointer.
     f32x2_t v[8];
+    const float* pc = plane + cell;
+    if (__all_sync(0xffffffffu, mask == 0xffu || n == 0)) {   // holes (n == 0) sit on cell 0: harmless reads
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float x = ((mask >> k) & 1u) ? __ldg(plane + cell + off[k]) : 0.f;
-      v[k] = pk2(x, x);
+      for (int k = 0; k < 8; ++k) {
+        const float x = PLANE_SMEM ? pc[off[k]] : __ldg(pc + off[k]);
+        v[k] = pk2(x, x);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float x = ((mask >> k) & 1u) ? (PLANE_SMEM ? pc[off[k]] : __ldg(pc + off[k])) : 0.f;
+        v[k] = pk2(x, x);
+      }
     }
     auto emit = [&](const TriPair t) {
       float lo, hi;
@@ -368,7 +449,7 @@ __global__ void __launch_bounds__(512, 2)
     };
     if (light) tri_walk(ra + (cur.h.y & 0xffffff), rb + (cur.h.y & 0xffffff), 0, (n + 1) >> 1, 2, 1, 32, dummy, emit);
     else tri_walk(ra + cur.h.y, rb + cur.h.y, lane, cur.h.z, 64, 32, 1, dummy, emit);
-    cur = nxt;
+    cur = take_cell_item(nxt);
   }
   __syncthreads();
   // ---- write the row: one bulk (TMA) store for the 16-byte aligned part, plain stores for the rest ----
@@ -379,15 +460,19 @@ __global__ void __launch_bounds__(512, 2)
     __syncthreads();
     if (threadIdx.x == 0) {
       for (uint32_t off2 = 0; off2 < (uint32_t)bulk * 4u; off2 += kBulkChunk)
-        bulk_s2g((char*)o + off2, (const char*)smem + off2, min(kBulkChunk, (uint32_t)bulk * 4u - off2));
+        bulk_s2g((char*)o + off2, (const char*)row + off2, min(kBulkChunk, (uint32_t)bulk * 4u - off2));
       bulk_commit();
     }
   }
-  for (int i = bulk + threadIdx.x; i < N; i += blockDim.x) o[i] = smem[i];
+  for (int i = bulk + threadIdx.x; i < N; i += blockDim.x) o[i] = row[i];
   if (bulk > 0 && threadIdx.x == 0) bulk_wait_read();  // the CTA may exit once the source has been read
 }
 
-static size_t tri_fwd_smem(int n) { return ((size_t)n + 4) * sizeof(float); }
+constexpr int kTriFwdPlaneMax = 8192;  // floats: planes up to r = 20 are staged in shared memory
+static size_t tri_fwd_smem(int n, int r = 0) {
+  const size_t p = (size_t)r * r * r;
+  return ((size_t)n + 4 + (p <= kTriFwdPlaneMax ? ((p + 3) & ~(size_t)3) : 0)) * sizeof(float);
+}
 
 // inds / wgts of the training-mode forward (trilinear_devox.cu:64-94), one thread per point
 __global__ void __launch_bounds__(256) tri_index_kernel(const float* __restrict__ coords, int* __restrict__ inds,
@@ -454,7 +539,7 @@ int pcfm_trilinear_devoxelize_backward_planned(const float* grad_y, int b, int c
 
 int pcfm_trilinear_devoxelize_forward_cells_ok(int b, int c, int n, int r) {
   if (b <= 0 || c <= 0 || n <= 0 || r <= 0) return 0;
-  return cellplan_fits(n, (long long)r * r * r, true) && tri_fwd_smem(n) <= kTriSmemLimit ? 1 : 0;
+  return cellplan_fits(n, (long long)r * r * r, true) && tri_fwd_smem(n, r) <= kTriSmemLimit ? 1 : 0;
 }
 
 int pcfm_trilinear_devoxelize_forward_cells(const float* coords, const float* features, int b, int c, int n, int r,
@@ -473,12 +558,26 @@ int pcfm_trilinear_devoxelize_forward_cells(const float* coords, const float* fe
   int rc = planned ? cellplan_attach(true, b, n, t, &plan, &ws)
                    : cellplan_build(nullptr, coords, r, nullptr, b, n, t, nullptr, &plan, &ws, st);
   if (rc) return rc;
-  if (c > 0) {
-    const size_t smem = tri_fwd_smem(n);
-    PCFM_CUDA(allow_dyn_smem((const void*)tri_fwd_kernel, (int)kTriSmemLimit));
-    PCFM_CUDA(launch_dependent(tri_fwd_kernel, dim3(c, b), dim3(512), smem, st, g_opt_pdl >= 2, features, plan.cells,
-                               plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec, (const float4*)plan.rec2,
-                               outs, c, n, r, plan.lcap, plan.hcap, plan.rcap, (int)(g_opt_stage == 0)));
+  if (c > 0 && (g_opt_tri2 == 1 || g_opt_tri2 == 2) && tri2_fwd_ok(c, n, r)) {
+    rc = launch_tri2_fwd(features, plan, outs, b, c, n, r, st);
+    if (rc) return rc;
+  } else if (c > 0) {
+    const size_t smem = tri_fwd_smem(n, r);
+    const bool ps = (long long)r * r * r <= kTriFwdPlaneMax;
+#define PCFM_TFWD(RT, PS)                                                                                           \
+  do {                                                                                                              \
+    PCFM_CUDA(allow_dyn_smem((const void*)tri_fwd_kernel<RT, PS>, (int)kTriSmemLimit));                             \
+    PCFM_CUDA(launch_dependent(tri_fwd_kernel<RT, PS>, dim3(c, b), dim3(512), smem, st, g_opt_pdl >= 2, features,   \
+                               plan.cells, plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec,              \
+                               (const float4*)plan.rec2, outs, c, n, r, plan.lcap, plan.hcap, plan.rcap,            \
+                               (int)(g_opt_stage == 0)));                                                           \
+  } while (0)
+    if (r == 32) PCFM_TFWD(32, false);
+    else if (r == 16) PCFM_TFWD(16, true);
+    else if (r == 8) PCFM_TFWD(8, true);
+    else if (ps) PCFM_TFWD(0, true);
+    else PCFM_TFWD(0, false);
+#undef PCFM_TFWD
     PCFM_LAUNCHED();
   }
   if (is_training) {

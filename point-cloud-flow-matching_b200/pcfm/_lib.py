@@ -54,6 +54,8 @@ SIGNATURES = {
     "pcfm_three_nn_interpolate_backward_workspace": (_sz, [_i, _i, _i, _i]),
     "pcfm_three_nn_interpolate_backward": (_i, [_p, _p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
     "pcfm_chamfer3d_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "pcfm_chamfer3d_forward_workspace": (_sz, [_i, _i, _i]),
+    "pcfm_chamfer3d_forward_ws": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _sz, _p]),
     "pcfm_chamfer3d_backward": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "pcfm_emd_approxmatch_workspace": (_sz, [_i, _i, _i]),
     "pcfm_emd_approxmatch_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _sz, _p]),

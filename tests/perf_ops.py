@@ -18,10 +18,32 @@ sys.path.insert(0, os.path.join(ROOT, "point-cloud-flow-matching_b200"))
 from pcfm import _lib, backend as be  # noqa: E402
 
 
+GRAPH = False
+
+
 def timeit(fn, iters=10, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
+    if GRAPH:   # the calls captured once and replayed: device time without the Python / ctypes launch path
+        st = torch.cuda.Stream()
+        st.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(st):
+            fn()
+        torch.cuda.current_stream().wait_stream(st)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / (3 * iters)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
@@ -45,7 +67,11 @@ def main():
     ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: r x N x C sweep (B=2)")
     ap.add_argument("--memo", type=int, default=0, help="1: leave the cell-plan memo on for every op (repeated calls on "
                     "the same coords then time the *_planned entries); default: off, planned entries timed as own ops")
+    ap.add_argument("--graph", action="store_true", help="time every op as a replayed CUDA graph of --iters calls "
+                    "(device time without the Python launch path; a *_planned op then includes 1/iters of a plan build)")
     args = ap.parse_args()
+    global GRAPH
+    GRAPH = args.graph
     only = set(args.only.split(",")) if args.only else None
     ref = None
     if args.ref:

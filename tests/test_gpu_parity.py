@@ -242,6 +242,49 @@ def test_trilinear_devoxelize(be, oracle, ref, kw):
                      atol_frac=1e-5)
 
 
+@pytest.mark.parametrize("kw", [DEVOX_SHAPES[0], DEVOX_SHAPES[2], DEVOX_SHAPES[3], DEVOX_SHAPES[6], DEVOX_SHAPES[14]],
+                         ids=lambda k: f"b{k['b']}c{k['c']}n{k['n']}r{k['res']}")
+def test_trilinear_walk_variants(be, oracle, kw):
+    """The optional walks (pcfm_set_option): tri2 = 1 two channels per persistent CTA (tri2.cu), bwd_phases = 1 light
+    cells added in 8 conflict-free corner phases instead of atomics — each against the oracle and the default kernels."""
+    from pcfm import _lib
+    coords, vox, gy, res = cases.devox_case(**kw)
+    o_outs, o_inds, o_wgts = oracle.trilinear_devoxelize_forward(res, coords, vox)
+    o_gx = oracle.trilinear_devoxelize_backward(gy, o_inds, o_wgts, res)
+    got = {}
+    for name, opts in (("default", {}), ("tri2", {"tri2": 1}), ("bwd_phases", {"bwd_phases": 1})):
+        for k, v in opts.items():
+            _lib.set_option(k, v)
+        try:
+            cc = cu(coords)
+            outs, inds, wgts = be.pvcnn.trilinear_devoxelize_forward(res, True, cc, cu(vox))
+            gx = be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), cc, res)          # plan left by the forward
+            gx2 = be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), cu(coords), res)  # fresh plan (PDL behind the build)
+        finally:
+            for k in opts:
+                _lib.set_option(k, 0)
+        assert_equal(host(inds), o_inds, f"inds ({name})")
+        assert_close(host(outs), o_outs, f"outs ({name})")
+        assert_close(host(gx), o_gx, f"grad_x ({name})", atol_frac=1e-5)
+        assert_close(host(gx2), o_gx, f"grad_x, fresh plan ({name})", atol_frac=1e-5)
+        got[name] = (host(outs), host(gx))
+    for name in ("tri2", "bwd_phases"):
+        assert_close(got[name][0], got["default"][0], f"outs: {name} vs default")
+        assert_close(got[name][1], got["default"][1], f"grad_x: {name} vs default", atol_frac=1e-5)
+    # the phased backward adds a voxel's light contributions in a fixed order: bit-identical run to run when no heavy
+    # cell (> 64 points, added with atomics) is involved
+    if kw["n"] <= 2048:
+        _lib.set_option("bwd_phases", 1)
+        try:
+            cc = cu(coords)
+            a = host(be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), cc, res))
+            b = host(be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), cc, res))
+        finally:
+            _lib.set_option("bwd_phases", 0)
+        if int(np.bincount(np.floor(coords[0]).astype(np.int64).T.dot([res * res, res, 1])).max()) <= 64:
+            assert_equal(a, b, "phased backward, run to run")
+
+
 def test_devox_backward_generic_is_deterministic(be):
     """Generic (inds/wgts) entry: sorted segmented sums, run-to-run bit-identical when no voxel receives more than
     64 contributions (csr.cu kMaxSortedSeg: those segments are put in ascending edge order)."""
@@ -381,6 +424,27 @@ def test_chamfer(be, oracle, ref, kw):
         rd1, rd2, ri1, ri2 = run_chamfer(ref["chamfer"], a, c)
         assert_equal(host(i1), host(ri1), "idx1 vs reference"); assert_equal(host(i2), host(ri2), "idx2 vs reference")
         assert_equal(host(d1), host(rd1), "dist1 vs reference"); assert_equal(host(d2), host(rd2), "dist2 vs reference")
+    # the two-pass entry without workspace (pcfm_chamfer3d_forward): same bits as the single-pass default
+    from pcfm import _lib
+    _lib.set_option("chamfer_once", 0)
+    try:
+        t1, t2, j1, j2 = run_chamfer(be.chamfer, a, c)
+    finally:
+        _lib.set_option("chamfer_once", 1)
+    assert_equal(host(j1), oi1, "idx1 (two-pass entry)"); assert_equal(host(j2), oi2, "idx2 (two-pass entry)")
+    assert_equal(host(t1), od1, "dist1 (two-pass entry)"); assert_equal(host(t2), od2, "dist2 (two-pass entry)")
+
+
+def test_chamfer_single_pass_large_lattice_ties(be, oracle):
+    """B=2, N=M=6000 lattice clouds (every distance tied many times): several row tiles AND several column tiles meet
+    in the 64-bit atomicMin keys; indices must still be the lowest among the ties."""
+    r = rng(77)
+    a = (r.integers(0, 9, size=(2, 6000, 3)) * 0.125).astype(np.float32)
+    c = (r.integers(0, 9, size=(2, 5000, 3)) * 0.125).astype(np.float32)
+    d1, d2, i1, i2 = run_chamfer(be.chamfer, a, c)
+    od1, od2, oi1, oi2 = oracle.chamfer_forward(a, c)
+    assert_equal(host(i1), oi1, "idx1"); assert_equal(host(i2), oi2, "idx2")
+    assert_equal(host(d1), od1, "dist1"); assert_equal(host(d2), od2, "dist2")
 
 
 def test_chamfer_same_cloud_is_zero(be):
