@@ -460,7 +460,7 @@ class _Chamfer3D:
         b, n, _ = xyz1.shape
         m = xyz2.shape[1]
         with torch.cuda.device(xyz1.device):
-            if _lib.options.get("chamfer_once", 1):   # every distance evaluated once for both directions
+            if _lib.options.get("chamfer_once", 1):   # from ~3e8 evaluations on: every distance evaluated once for both directions
                 ws = _ws(lib.pcfm_chamfer3d_forward_workspace(b, n, m), xyz1.device)
                 rc = lib.pcfm_chamfer3d_forward_ws(_ptr(xyz1), _ptr(xyz2), b, n, m, _ptr(dist1), _ptr(dist2),
                                                    _ptr(idx1), _ptr(idx2), _ptr(ws), ws.numel(), _stream(xyz1))

@@ -424,15 +424,17 @@ def test_chamfer(be, oracle, ref, kw):
         rd1, rd2, ri1, ri2 = run_chamfer(ref["chamfer"], a, c)
         assert_equal(host(i1), host(ri1), "idx1 vs reference"); assert_equal(host(i2), host(ri2), "idx2 vs reference")
         assert_equal(host(d1), host(rd1), "dist1 vs reference"); assert_equal(host(d2), host(rd2), "dist2 vs reference")
-    # the two-pass entry without workspace (pcfm_chamfer3d_forward): same bits as the single-pass default
+    # chamfer_once: 0 = the two directional passes (pcfm_chamfer3d_forward), 2 = the single pass whatever the size
+    # (the default picks by size); same bits either way
     from pcfm import _lib
-    _lib.set_option("chamfer_once", 0)
-    try:
-        t1, t2, j1, j2 = run_chamfer(be.chamfer, a, c)
-    finally:
-        _lib.set_option("chamfer_once", 1)
-    assert_equal(host(j1), oi1, "idx1 (two-pass entry)"); assert_equal(host(j2), oi2, "idx2 (two-pass entry)")
-    assert_equal(host(t1), od1, "dist1 (two-pass entry)"); assert_equal(host(t2), od2, "dist2 (two-pass entry)")
+    for opt in (0, 2):
+        _lib.set_option("chamfer_once", opt)
+        try:
+            t1, t2, j1, j2 = run_chamfer(be.chamfer, a, c)
+        finally:
+            _lib.set_option("chamfer_once", 1)
+        assert_equal(host(j1), oi1, f"idx1 (chamfer_once={opt})"); assert_equal(host(j2), oi2, f"idx2 (chamfer_once={opt})")
+        assert_equal(host(t1), od1, f"dist1 (chamfer_once={opt})"); assert_equal(host(t2), od2, f"dist2 (chamfer_once={opt})")
 
 
 def test_chamfer_single_pass_large_lattice_ties(be, oracle):
@@ -441,7 +443,12 @@ def test_chamfer_single_pass_large_lattice_ties(be, oracle):
     r = rng(77)
     a = (r.integers(0, 9, size=(2, 6000, 3)) * 0.125).astype(np.float32)
     c = (r.integers(0, 9, size=(2, 5000, 3)) * 0.125).astype(np.float32)
-    d1, d2, i1, i2 = run_chamfer(be.chamfer, a, c)
+    from pcfm import _lib
+    _lib.set_option("chamfer_once", 2)
+    try:
+        d1, d2, i1, i2 = run_chamfer(be.chamfer, a, c)
+    finally:
+        _lib.set_option("chamfer_once", 1)
     od1, od2, oi1, oi2 = oracle.chamfer_forward(a, c)
     assert_equal(host(i1), oi1, "idx1"); assert_equal(host(i2), oi2, "idx2")
     assert_equal(host(d1), od1, "dist1"); assert_equal(host(d2), od2, "dist2")

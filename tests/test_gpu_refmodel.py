@@ -172,16 +172,26 @@ def test_hybridmlp_matches_the_reference_extension(models):
         backend.plan_memo.clear()
         try:
             v_ref, g_ref = run()
+            v_ref2, g_ref2 = run()      # the reference against itself: its atomics make it order-dependent
         finally:
             PF._backend = ours
     finally:
         torch.backends.cudnn.allow_tf32, torch.backends.cudnn.deterministic = old_tf32, old_det
     err = (v_ours - v_ref).abs().max().item() / max(v_ref.abs().max().item(), 1e-30)
     assert err <= 1e-4, f"velocity differs from the reference extension: {err:.3e}"
-    worst = 0.0
-    for a, b in zip(g_ours, g_ref):
+    # Gradients: compared on the parameters that HAVE one — a convolution bias in front of a BatchNorm has gradient
+    # exactly 0 and both backends return rounding noise of ~1e-8 there (the reference differs from ITSELF by 100 % on
+    # those).  The reference adds with order-free atomics, so two of its own runs differ by ~1e-4 on the others.
+    gmax = max(float(b.abs().max()) for b in g_ref if b is not None)
+    worst, noise, n_cmp = 0.0, 0.0, 0
+    for a, b, b2 in zip(g_ours, g_ref, g_ref2):
         assert (a is None) == (b is None)
-        if a is not None and b.abs().max() > 0:
+        if a is not None and float(b.abs().max()) >= 1e-4 * gmax:
             worst = max(worst, (a - b).abs().max().item() / b.abs().max().item())
-    assert worst <= 2e-3, f"parameter gradients differ from the reference extension: {worst:.3e}"
-    print(f"HybridMLP vs reference extension: velocity {err:.2e}, worst gradient {worst:.2e}")
+            noise = max(noise, (b2 - b).abs().max().item() / b.abs().max().item())
+            n_cmp += 1
+    print(f"HybridMLP vs reference extension: velocity {err:.2e}, worst gradient {worst:.2e} over {n_cmp} parameters; "
+          f"reference vs itself {noise:.2e}")
+    assert n_cmp >= 100, f"only {n_cmp} parameters carried a gradient"
+    assert worst <= max(2e-3, 5 * noise), (f"parameter gradients differ from the reference extension: {worst:.3e} "
+                                           f"(the reference differs from itself by {noise:.3e})")
