@@ -588,11 +588,22 @@ def run_ours(args):
                 return m0.elapsed_time(m1) / n_it, _lib.launch_count() / n_it
 
             ms_mod, launches_mod = time_module(5)
+            # the same pyramid with the voxel grids in channels_last_3d (NDHWC) for the cuDNN layers
+            PVConv.channels_last = True
+            try:
+                net_cl = net.to(memory_format=torch.channels_last_3d)
+                ms_cl, _ = time_module(5)
+            finally:
+                PVConv.channels_last = False
+                net.to(memory_format=torch.contiguous_format)
             module = {"what": "SharedMLP projections + 6 PVConv blocks (Conv3d/BatchNorm3d/SE through cuDNN/cuBLAS, TF32 "
                               "conv default) of ContextNet on ONE shared coords tensor, forward + backward, B=8, N=20000",
                       "ms_fwd_bwd": ms_mod, "mpts_per_s": B * NPTS * len(STAGES) / ms_mod / 1e3,
                       "pcfm_launches_per_step": launches_mod,
-                      "primitive_share": round(ms_per_step / ms_mod, 3)}
+                      "primitive_share": round(ms_per_step / ms_mod, 3),
+                      "ms_fwd_bwd_channels_last": ms_cl,
+                      "channels_last": "PVConv.channels_last = True: voxel grids in torch.channels_last_3d for Conv3d / "
+                                       "BatchNorm3d / SE (cuDNN NDHWC kernels), NCDHW for the point-voxel primitives"}
             del net, mf, mc
             torch.cuda.empty_cache()
         except Exception as e:  # noqa: BLE001

@@ -37,6 +37,7 @@ extern int g_opt_bwd_phases;    // devoxelize backward, light cells: 0 = shared-
 extern int g_opt_dbg;           // measurement only (tri2 forward): 1 skip light slices, 2 skip heavy pieces, 4 no row stores
 extern int g_opt_chamfer_once;  // pcfm_chamfer3d_forward_ws: 1 = single pass from ~3e8 distance evaluations on (default), 2 = always,
                                 // 0 = never (pcfm/backend.py then calls the two-pass entry)
+extern int g_opt_emd_cluster;   // approxmatch operator: 1 = cluster of 8 CTAs per batch element (default), 0 = one CTA
 extern int g_opt_plan;          // 0 = fused cell-plan build when it fits, 1 = always the multi-kernel build
 extern int g_num_sms;           // cached SM count of the current device (148 on B200)
 int num_sms();

@@ -17,6 +17,7 @@ int g_opt_devox_fwd = 0;
 int g_opt_tri2 = 0;
 int g_opt_bwd_phases = 0;
 int g_opt_dbg = 0;
+int g_opt_emd_cluster = 1;
 int g_opt_chamfer_once = 1;
 int g_opt_gather_bwd = 0;
 int g_opt_fps = 0;
@@ -87,6 +88,7 @@ int pcfm_set_option(const char* key, int value) {
   if (!strcmp(key, "tri2")) { pcfm::g_opt_tri2 = value; return 0; }
   if (!strcmp(key, "dbg")) { pcfm::g_opt_dbg = value; return 0; }
   if (!strcmp(key, "bwd_phases")) { pcfm::g_opt_bwd_phases = value; return 0; }
+  if (!strcmp(key, "emd_cluster")) { pcfm::g_opt_emd_cluster = value; return 0; }
   if (!strcmp(key, "chamfer_once")) { pcfm::g_opt_chamfer_once = value; return 0; }
   return PCFM_E_BADARG;
 }

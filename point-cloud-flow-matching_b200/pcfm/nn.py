@@ -137,7 +137,16 @@ class SE3d(nn.Module):
 class PVConv(nn.Module):
     """Point-voxel convolution (pvconv.py:11-39): voxelize -> 2x(Conv3d,BN3d,LeakyReLU)[+SE] -> devoxelize,
     fused with a point-wise SharedMLP branch.  forward((features[B,Cin,N], coords[B,3,N])) -> (features, coords).
+
+    `PVConv.channels_last` (class attribute, default False): the voxel grid is handed to the Conv3d /
+    BatchNorm3d stack in torch.channels_last_3d memory format (NDHWC), where cuDNN runs its tensor-core kernels; the
+    grid comes back to the reference's NCDHW layout in front of the devoxelization, so the point-voxel primitives, the
+    parameters and the results are unchanged (same values up to cuDNN's algorithm choice).  It is a host-side layout
+    switch around library calls: two extra transposes of the grid per block and direction, paid back by the faster
+    convolutions (bench.py `pvconv_modules`).
     """
+
+    channels_last = False
 
     def __init__(self, in_channels, out_channels, kernel_size, resolution, with_se=False, normalize=True, eps=0):
         super().__init__()
@@ -157,7 +166,11 @@ class PVConv(nn.Module):
     def forward(self, inputs):
         features, coords = inputs
         grid, vcoords = self.voxelization(features, coords)
-        grid = self.voxel_layers(grid)
+        if PVConv.channels_last and grid.is_cuda:
+            grid = self.voxel_layers(grid.contiguous(memory_format=torch.channels_last_3d))
+            grid = grid.contiguous(memory_format=torch.contiguous_format)   # the primitives keep the reference layout
+        else:
+            grid = self.voxel_layers(grid)
         from_voxels = F.trilinear_devoxelize(grid, vcoords, self.resolution, self.training)
         return from_voxels + self.point_features(features), coords
 

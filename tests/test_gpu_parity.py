@@ -301,6 +301,91 @@ def test_devox_backward_generic_is_deterministic(be):
     assert_close(c, a, "coords entry vs generic entry", rtol=1e-6, atol_frac=1e-6)
 
 
+def test_pvconv_channels_last_voxel_grids(be):
+    """PVConv.channels_last: Conv3d / BatchNorm3d / SE see the voxel grid in channels_last_3d; the block's
+    output and the parameter gradients are those of the NCDHW run (TF32 off: only cuDNN's algorithm choice differs)."""
+    from pcfm.nn import PVConv
+    torch.manual_seed(0)
+    blk = PVConv(32, 32, 3, 16, with_se=True, normalize=True, eps=1e-6).cuda().train()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    f = torch.randn(2, 32, 3000, device="cuda", generator=g, requires_grad=True)
+    c = torch.randn(2, 3, 3000, device="cuda", generator=g)
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        res = []
+        for cl in (False, True):
+            PVConv.channels_last = cl
+            blk.zero_grad(set_to_none=True)
+            f.grad = None
+            for m in blk.modules():
+                if isinstance(m, torch.nn.BatchNorm3d) or isinstance(m, torch.nn.BatchNorm1d):
+                    m.reset_running_stats()
+            out, _ = blk((f, c))
+            out.square().mean().backward()
+            res.append((out.detach().clone(), f.grad.clone(), blk.voxel_layers[0].weight.grad.clone()))
+    finally:
+        PVConv.channels_last = False
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+    for a, b, what in zip(res[1], res[0], ("output", "feature gradient", "conv weight gradient")):
+        err = float((a - b).abs().max() / b.abs().max())
+        assert err <= 1e-4, f"channels_last {what}: {err:.2e}"
+
+
+# ------------------------------------------------------------------------------------------------ bench shapes
+@pytest.mark.parametrize("c,res", [(128, 32), (256, 16), (256, 8)], ids=lambda v: str(v))
+def test_pvconv_chain_at_the_bench_shapes_against_the_reference_kernels(be, ref, c, res):
+    """BASELINE config 2 exactly (B=8, N=20000, Gaussian clouds through the reference normalisation): the four
+    primitives of a PVConv block against the UNMODIFIED reference kernels (oracle/_ref) on the same GPU.  Integer
+    outputs bit-exact.  Values: the reference adds with order-free atomics, so it is first compared with ITSELF (two
+    runs); this library must agree with it within max(1e-5, that spread) normwise — and the gather-type ops (avg_voxelize
+    backward, devoxelize forward), where nothing is order-dependent, within 1e-6 / 1e-5 as usual."""
+    R = ref["pvcnn"]
+    if R is None:
+        pytest.skip("oracle/_ref/pvcnn not built")
+    b, n = 8, 20000
+    g = torch.Generator(device="cuda").manual_seed(1000 + res)
+    feat = torch.randn(b, c, n, device="cuda", generator=g)
+    coords = torch.randn(b, 3, n, device="cuda", generator=g)
+    nc = coords - coords.mean(2, keepdim=True)
+    nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 1e-6) + 0.5
+    nc = torch.clamp(nc * res, 0, res - 1).contiguous()
+    vox = torch.round(nc).to(torch.int32).contiguous()
+    grid = torch.randn(b, c, res ** 3, device="cuda", generator=g)
+    gy = torch.randn(b, c, n, device="cuda", generator=g)
+
+    def spread(x, y):
+        return float((x - y).abs().max() / y.abs().max())
+
+    P = be.pvcnn
+    out, ind, cnt = P.avg_voxelize_forward(feat, vox, res, nc)
+    r_out, r_ind, r_cnt = R.avg_voxelize_forward(feat, vox, res)
+    r_out2 = R.avg_voxelize_forward(feat, vox, res)[0]
+    assert torch.equal(ind, r_ind) and torch.equal(cnt, r_cnt), "ind / cnt"
+    noise = spread(r_out2, r_out)
+    assert spread(out, r_out) <= max(1e-5, 2 * noise), f"avg_voxelize: {spread(out, r_out):.2e} (reference vs itself {noise:.2e})"
+    report = {"vox_fwd": (spread(out, r_out), noise)}
+
+    outs, inds, wgts = P.trilinear_devoxelize_forward(res, True, nc, grid)
+    r_outs, r_inds, r_wgts = R.trilinear_devoxelize_forward(res, True, nc, grid)
+    assert torch.equal(inds, r_inds) and torch.equal(wgts, r_wgts), "inds / wgts"
+    assert_close(host(outs), host(r_outs), "devoxelize forward")
+    report["devox_fwd"] = (spread(outs, r_outs), 0.0)
+
+    gg = P.trilinear_devoxelize_backward_coords(gy, nc, res)
+    r_gg = R.trilinear_devoxelize_backward(gy, r_inds, r_wgts, res)
+    r_gg2 = R.trilinear_devoxelize_backward(gy, r_inds, r_wgts, res)
+    noise = spread(r_gg2, r_gg)
+    assert spread(gg, r_gg) <= max(1e-5, 2 * noise), f"devoxelize backward: {spread(gg, r_gg):.2e} (reference vs itself {noise:.2e})"
+    report["devox_bwd"] = (spread(gg, r_gg), noise)
+    assert torch.equal(gg != 0, r_gg != 0), "sparsity pattern of the devoxelize gradient"
+
+    gf = P.avg_voxelize_backward(grid, ind, cnt)
+    r_gf = R.avg_voxelize_backward(grid, r_ind, r_cnt)
+    assert_equal(host(gf), host(r_gf), "avg_voxelize backward (a gather: bit-exact)")
+    print(f"bench shape C={c} r={res}: " + ", ".join(f"{k} {a:.1e} (ref vs ref {e:.1e})" for k, (a, e) in report.items()))
+
+
 # ------------------------------------------------------------------------------------------------ pointnet ops
 PN_SHAPES = [
     dict(seed=41, b=2, c=5, n=1024, m=256, kind="rand"),
@@ -567,6 +652,31 @@ def test_emd(be, oracle, ref, kw):
         assert_close(host(match), host(r_match), "match vs reference", rtol=2e-5, atol_frac=2e-6)
         rg1, rg2 = ref["emd"].matchcost_backward(cu(gc), cu(a), cu(c), r_match)
         assert_close(host(g1), host(rg1), "grad1 vs reference"); assert_close(host(g2), host(rg2), "grad2 vs reference")
+    # the cluster kernel (8 CTAs per batch element, default from 256 points) deals ROWS to the CTAs and leaves every
+    # row's summation order alone: bit-identical to the one-CTA kernel
+    from pcfm import _lib
+    _lib.set_option("emd_cluster", 0)
+    try:
+        one = be.emd.approxmatch_forward(cu(a), cu(c))
+    finally:
+        _lib.set_option("emd_cluster", 1)
+    assert_equal(host(match), host(one), "match: cluster kernel vs one CTA per batch element")
+
+
+def test_emd_cluster_kernel_shapes(be):
+    """Cluster approxmatch at the README shape (B=2, N=1024), at B=8 x 2048 and on ragged sizes: bit-identical to the
+    one-CTA kernel, doubly stochastic up to the auction's tolerance."""
+    from pcfm import _lib
+    for (b, n, m, seed) in [(2, 1024, 1024, 1), (8, 2048, 2048, 2), (3, 1500, 700, 3), (2, 300, 2100, 4), (1, 9000, 9000, 5)]:
+        r = rng(seed)
+        a = r.random((b, n, 3)).astype(np.float32); c = r.random((b, m, 3)).astype(np.float32)
+        got = be.emd.approxmatch_forward(cu(a), cu(c))
+        _lib.set_option("emd_cluster", 0)
+        try:
+            one = be.emd.approxmatch_forward(cu(a), cu(c))
+        finally:
+            _lib.set_option("emd_cluster", 1)
+        assert torch.equal(got, one), f"B={b} N={n} M={m}"
 
 
 def test_emd_known_answer(be):
