@@ -44,10 +44,11 @@ CONFIG = {
                 "(C,r) = 2x(128,32) 2x(256,16) 2x(256,8); vox fwd + devox fwd(train) + devox bwd + vox bwd per instance",
     "batch": B, "points": NPTS, "stages": STAGES,
     "plans": "the two PVConv blocks of a stage share one coords tensor (models.py:385-389), so the second block's "
-             "avg_voxelize forward / devoxelize backward reuse the first block's cell plans (pcfm_*_planned); the first "
-             "avg_voxelize of a stage builds the mean AND the trilinear plan in one launch "
-             "(pcfm_avg_voxelize_forward_dual, what pcfm.nn.Voxelization calls in a training pass); the plan memo is "
-             "cleared at the start of EVERY step (new point clouds every training step): 3 dual builds per step",
+             "avg_voxelize forward / devoxelize forward / devoxelize backward reuse the first block's cell plans "
+             "(pcfm_*_planned, pcfm_trilinear_devoxelize_forward_cells); the first avg_voxelize of a stage builds the "
+             "mean AND the trilinear plan in one launch (pcfm_avg_voxelize_forward_dual, what pcfm.nn.Voxelization "
+             "calls); the plan memo is cleared at the start of EVERY step (new point clouds every training step): "
+             "3 dual builds per step",
     "l2": "inputs larger than L2: ~4.8 GB touched per step, every primitive reads tensors not written in that step",
     "parallelism": "one process per GPU, replicas (data parallel), no data-path collective",
 }
@@ -470,14 +471,14 @@ def run_ours(args):
     tot_bytes = sum(algorithmic_bytes(n_, c, r) * len(ts) / 3 for (n_, c, r), ts in per.items())
     traffic = None
     try:  # dram__bytes_read.sum + dram__bytes_write.sum of that op's main kernel, one launch, from the committed capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01c_ncu_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")))
         traffic = tj["dram_bytes_per_launch"].get(f"{top['op']},{top['C']},{top['r']}")
     except Exception:  # noqa: BLE001
         pass
     roofline = {"bound": "hbm", "kernel": f"{top['op']} C={top['C']} r={top['r']} (op = row kernel + its share of the stage's plan build: "
                           "mean over the two blocks of the stage)",
                 "achieved": top["GBps"], "peak": peak, "unit": "GB/s", "frac": round(top["GBps"] / peak, 4),
-                "traffic": traffic, "traffic_source": "profiles/r01c_ncu_traffic.json (ncu --set full, same shapes)",
+                "traffic": traffic, "traffic_source": "profiles/r02_ncu_traffic.json (ncu --set full, same shapes, main kernel of the op)",
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": top_bytes,
                 "step_aggregate": {"algorithmic_GB_per_step": round(tot_bytes / 1e9, 3),
                                    "achieved_GBps": round(tot_bytes / (ms_per_step * 1e-3) / 1e9 * 1.0, 1),

@@ -17,7 +17,7 @@ import sys
 
 SHAPES = {"s1": (128, 32), "s2": (256, 16), "s3": (256, 8)}
 MAIN = {"vox_fwd_cell_kernel": "vox_fwd", "devox_fwd_kernel": "devox_fwd", "devox_bwd_cell_kernel": "devox_bwd",
-        "row_gather_kernel": "vox_bwd"}
+        "row_gather_kernel": "vox_bwd", "tri_fwd_kernel": "devox_fwd", "tri_bwd_kernel": "devox_bwd"}   # r02: tri.cu walks
 COLS = {
     "gpu__time_duration.sum": "time_us",
     "dram__bytes_read.sum": "dram_read_MB",
@@ -28,6 +28,8 @@ COLS = {
     "launch__registers_per_thread": "regs",
     "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed": "smem_wavefront_pct",
     "lts__throughput.avg.pct_of_peak_sustained_elapsed": "l2_throughput_pct",
+    "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed": "l1_data_pipe_wavefront_pct",
+    "smsp__inst_executed.sum": "warp_inst_executed",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio": "stall_long_scoreboard",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio": "stall_short_scoreboard",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio": "stall_barrier",

@@ -64,7 +64,8 @@ def main():
     ap.add_argument("--warm", type=int, default=3, help="untimed calls before the timed ones (0 for ncu captures)")
     ap.add_argument("--opt", default="", help="extra pcfm_set_option pairs, e.g. devox_rep=0,stage=1")
     ap.add_argument("--plan", type=int, default=0, help="pcfm_set_option('plan', .): 1 = multi-kernel cell-plan build")
-    ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: r x N x C sweep (B=2)")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: r x N x C sweep")
+    ap.add_argument("--sweep-batch", type=int, default=8, help="batch size of the config-5 sweep")
     ap.add_argument("--memo", type=int, default=0, help="1: leave the cell-plan memo on for every op (repeated calls on "
                     "the same coords then time the *_planned entries); default: off, planned entries timed as own ops")
     ap.add_argument("--graph", action="store_true", help="time every op as a replayed CUDA graph of --iters calls "
@@ -87,7 +88,8 @@ def main():
     rows = []
     shapes = [("s1", 128, 32, B, N), ("s2", 256, 16, B, N), ("s3", 256, 8, B, N), ("c1", 64, 32, 2, 2048)]
     if args.sweep:
-        shapes = [(f"c5_r{r}_n{n}_c{c}", c, r, 2, n) for r in (16, 32, 64) for n in (10000, 20000, 100000) for c in (64, 256)]
+        shapes = [(f"c5_r{r}_n{n}_c{c}", c, r, args.sweep_batch, n)
+                  for r in (16, 32, 64) for n in (10000, 20000, 100000) for c in (64, 256)]
     for name, c, r, b, n in shapes:
         if only and name not in only:
             continue
@@ -108,6 +110,15 @@ def main():
         s = r ** 3
         byt = {"vox_fwd": 4 * b * (c * n + 3 * n + c * s + n + s), "vox_bwd": 4 * b * (c * s + n + s + c * n),
                "devox_fwd": 4 * b * (3 * n + c * s + c * n + 16 * n), "devox_bwd": 4 * b * (c * n + 16 * n + c * s)}
+        # sparse-aware denominators ("when N < r^3 the grid term dominates ... report both"): the gather-type
+        # ops only READ the voxels that hold points (avg_voxelize backward) / the corners around them (devoxelize
+        # forward); grids that are WRITTEN (avg_voxelize forward, devoxelize backward) stay dense, zeros included
+        occ = int((cnt > 0).sum())                                   # occupied voxels, summed over the batch
+        corners = sum(int(torch.unique(inds[i]).numel()) for i in range(b))
+        byt_sparse = {"vox_bwd": 4 * (c * occ + b * n + occ + b * c * n),
+                      "devox_fwd": 4 * (b * 3 * n + c * corners + b * c * n + b * 16 * n)}
+        for k in ("vox_bwd", "devox_fwd"):
+            byt_sparse[k + "_planned"] = byt_sparse[k]
         feat0 = feat[:, :0].contiguous()
         ops = {
             "plan_mean": lambda: P.avg_voxelize_forward(feat0, vox, r),     # C == 0: the cell-plan build alone
@@ -146,17 +157,18 @@ def main():
             if op in byt:
                 row["GBps"] = round(byt[op] / ms / 1e6, 1)
                 row["frac_of_6545"] = round(byt[op] / ms / 1e6 / 6545.3, 4)
-            if args.no_variants:
-                rows.append(row); print(json.dumps(row), flush=True)
-                continue
-            if op == "vox_fwd":
-                _lib.set_option("vox_fwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4)
-                _lib.set_option("vox_fwd", 2); row["ms_csr_variant"] = round(timeit(fn), 4); _lib.set_option("vox_fwd", 0)
-            if op == "devox_bwd_generic":
-                _lib.set_option("devox_bwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4); _lib.set_option("devox_bwd", 0)
-            if op in ("vox_fwd", "devox_fwd"):
-                _lib.set_option("stage", 1); row["ms_plain_stage"] = round(timeit(fn), 4); _lib.set_option("stage", 0)
-            if ref and ref["pvcnn"] is not None and op != "plan_mean":
+            if op in byt_sparse:
+                row["frac_of_6545_sparse_aware"] = round(byt_sparse[op] / ms / 1e6 / 6545.3, 4)
+            if not args.no_variants:
+                if op == "vox_fwd":
+                    _lib.set_option("vox_fwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4)
+                    _lib.set_option("vox_fwd", 2); row["ms_csr_variant"] = round(timeit(fn), 4); _lib.set_option("vox_fwd", 0)
+                if op == "devox_bwd_generic":
+                    _lib.set_option("devox_bwd", 1); row["ms_atomic_variant"] = round(timeit(fn), 4); _lib.set_option("devox_bwd", 0)
+                if op in ("vox_fwd", "devox_fwd"):
+                    _lib.set_option("stage", 1); row["ms_plain_stage"] = round(timeit(fn), 4); _lib.set_option("stage", 0)
+            if ref and ref["pvcnn"] is not None and op in ("vox_fwd", "vox_bwd", "devox_fwd", "devox_fwd_eval", "devox_bwd",
+                                                           "devox_bwd_generic"):
                 R = ref["pvcnn"]
                 rf = {"vox_fwd": lambda: R.avg_voxelize_forward(feat, vox, r),
                       "vox_bwd": lambda: R.avg_voxelize_backward(grid, ind, cnt),
@@ -171,7 +183,7 @@ def main():
         only = {"none"}
     if only and "pointnet" in only:
         # SURVEY 8(a) rows a8-a11 at the config-5 sizes: N points, M = N/4 centres (FPS), U = 32 neighbours, C = 64
-        for (b, n, c) in [(8, 4096, 64), (8, 20000, 64), (2, 100000, 64)]:
+        for (b, n, c) in [(8, 4096, 64), (8, 10000, 64), (8, 20000, 64), (8, 100000, 64)]:
             m, u = n // 4, 32
             pts = torch.rand(b, 3, n, device=dev, generator=g) * 2 - 1
             feat = torch.randn(b, c, n, device=dev, generator=g)
@@ -205,6 +217,13 @@ def main():
                 if op == "ball_query":
                     row["neighbours_found_mean"] = round(float((nb != nb[..., :1]).float().sum(-1).mean()) + 1, 2)
                     row["Gevals_per_s_worst_case"] = round(b * m * n / row["ms"] / 1e6, 1)
+                    # early exit: a centre stops scanning at its U-th hit (ball_query.cu:36); with fewer hits the tail
+                    # of the row repeats the first one and the whole cloud was scanned
+                    full = nb[..., -1] != nb[..., 0]
+                    scanned = torch.where(full, nb[..., -1].float() + 1, torch.full_like(nb[..., -1], n).float())
+                    row["scanned_fraction"] = round(float(scanned.mean()) / n, 4)
+                    row["Gevals_per_s_actual"] = round(b * m * n * row["scanned_fraction"] / row["ms"] / 1e6, 1)
+                    row["radius"] = radius
                 if op == "three_nn_fwd":
                     row["Gevals_per_s"] = round(b * m * n / row["ms"] / 1e6, 1)
                 if rfn is not None:
