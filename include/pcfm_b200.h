@@ -272,15 +272,6 @@ size_t pcfm_emd_allpairs_workspace(int ns, int nr, int n, int m);
 int pcfm_emd_allpairs(const float* s, const float* r, int ns, int nr, int n, int m, float* emd,
                       void* workspace, size_t workspace_bytes, pcfm_stream_t stream);
 
-/* ------------------------------------------------------------------------------------------------
- * Host-buffer convenience entry points (pageable or pinned HOST pointers; the copies run on `stream`
- * inside the call and the call returns after the results are in the host buffers).
- * ---------------------------------------------------------------------------------------------- */
-int pcfm_chamfer3d_forward_host(const float* xyz1_host, const float* xyz2_host, int b, int n, int m,
-                                float* dist1_host, float* dist2_host, int* idx1_host, int* idx2_host);
-int pcfm_avg_voxelize_forward_host(const float* features_host, const int* coords_host, int b, int c, int n, int r,
-                                   float* out_host, int* ind_host, int* cnt_host);
-
 #ifdef __cplusplus
 }
 #endif

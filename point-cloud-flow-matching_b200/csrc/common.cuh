@@ -30,11 +30,8 @@ extern int g_opt_fps;           // 0 = cluster FPS (points in registers) when th
 extern int g_opt_gather_bwd;    // 0 = gather backward with atomics (like the reference), 1 = sorted-segment sums
 extern int g_opt_devox_fwd;     // 0 = devoxelize forward as a walk over the trilinear cell plan when the caller offers a
                                 // workspace (default), 1 = always the plane-staging point-lane kernels
-extern int g_opt_tri2;          // two-channel persistent trilinear walks (tri2.cu): 0 = off (default: measured slower, see
-                                // tri2.cu), 1 = forward and backward, 2 = forward only, 3 = backward only
-extern int g_opt_bwd_phases;    // devoxelize backward, light cells: 0 = shared-memory atomics (default), 1 = static rounds +
-                                // 8 conflict-free corner phases (deterministic order; measured 0-15 % slower: barrier stalls)
-extern int g_opt_dbg;           // measurement only (tri2 forward): 1 skip light slices, 2 skip heavy pieces, 4 no row stores
+extern int g_opt_bwd_phases;    // devoxelize backward, how light cells reach the plane: 0 = shared-memory atomics (default),
+                                // 2 = deferred conflict-free corner phases: fixed summation order, not faster (tri.cu)
 extern int g_opt_chamfer_once;  // pcfm_chamfer3d_forward_ws: 1 = single pass from ~3e8 distance evaluations on (default), 2 = always,
                                 // 0 = never (pcfm/backend.py then calls the two-pass entry)
 extern int g_opt_emd_cluster;   // approxmatch operator: 1 = cluster of 8 CTAs per batch element (default), 0 = one CTA

@@ -14,9 +14,7 @@ int g_opt_vox_fwd = 0;
 int g_opt_stage = 0;
 int g_opt_plan = 0;
 int g_opt_devox_fwd = 0;
-int g_opt_tri2 = 0;
 int g_opt_bwd_phases = 0;
-int g_opt_dbg = 0;
 int g_opt_emd_cluster = 1;
 int g_opt_chamfer_once = 1;
 int g_opt_gather_bwd = 0;
@@ -85,8 +83,6 @@ int pcfm_set_option(const char* key, int value) {
   if (!strcmp(key, "gather_bwd")) { pcfm::g_opt_gather_bwd = value; return 0; }
   if (!strcmp(key, "plan")) { pcfm::g_opt_plan = value; return 0; }
   if (!strcmp(key, "devox_fwd")) { pcfm::g_opt_devox_fwd = value; return 0; }
-  if (!strcmp(key, "tri2")) { pcfm::g_opt_tri2 = value; return 0; }
-  if (!strcmp(key, "dbg")) { pcfm::g_opt_dbg = value; return 0; }
   if (!strcmp(key, "bwd_phases")) { pcfm::g_opt_bwd_phases = value; return 0; }
   if (!strcmp(key, "emd_cluster")) { pcfm::g_opt_emd_cluster = value; return 0; }
   if (!strcmp(key, "chamfer_once")) { pcfm::g_opt_chamfer_once = value; return 0; }

@@ -12,13 +12,6 @@
 
 namespace pcfm {
 
-// tri2.cu: two channels per CTA, persistent
-bool tri2_fwd_ok(int c, int n, int r);
-bool tri2_bwd_ok(int c, int n, int r);
-int launch_tri2_fwd(const float* vox, const CellPlan& plan, float* outs, int b, int c, int n, int r, cudaStream_t st);
-int launch_tri2_bwd(const float* grad_y, const CellPlan& plan, float* grad_x, int b, int c, int n, int r, bool reused,
-                    cudaStream_t st);
-
 constexpr size_t kTriSmemLimit = 227 * 1024 - 512;  // opt-in maximum (232448 B) minus the static shared memory
 
 // ---- the two points of a pair slot -------------------------------------------------------------------------------
@@ -188,54 +181,25 @@ __global__ void __launch_bounds__(1024, 1)
   const int nslice = l1 >> 5, nitem = nslice + h1;
   const int4* hv = (const int4*)heavy + (long long)b * hcap;
   const int nw = blockDim.x >> 5, warp = threadIdx.x >> 5;
-  // ---- light cells (sliced-ELL, one thread per cell): the 8 corner sums of a cell's points are built in registers.
-  // Neighbouring cells share voxels, so adding them to the plane needs care.  A shared-memory float atomicAdd is a CAS
-  // loop whose 32 lanes are served one by one (ncu: ~30 wavefronts per warp instruction, two thirds of all shared-memory
-  // traffic of the kernel).  With `phases` (pcfm_set_option("bwd_phases", 1)) the slices are dealt to the warps in ROUNDS
-  // (slice = round * warps + warp: count-sorted, so the slices of a round are equally long) and after every round the
-  // CTA adds corner 0 of all its cells, then corner 1, ... : cell -> cell + offset(k) is injective, so inside a phase
-  // no two threads touch the same voxel and the add is a plain load / add / store.  8 barriers per round, ~2-4 rounds
-  // per row; a voxel's light contributions then arrive in a fixed order.  Measured (B=8, N=20000): the atomics' wavefronts
-  // are gone but the barriers stall as long (r=32: 0.136 -> 0.135 ms, r=16: 0.130 -> 0.143, r=8: 0.110 -> 0.122), so the
-  // atomic walk below stays the default.
-  const bool phased = PLANE_SMEM && phases != 0;
-  if (phased) {
-    int hx = 0, hy = 0;
-    if (warp < nslice) {
-      hx = __ldg(cl + ((warp << 5) | lane));
-      hy = __ldg(sl + ((warp << 5) | lane));
-    }
-    for (int rd = 0; rd * nw < nslice; ++rd) {
-      const int n = (int)((unsigned)hx >> 24);  // 0 = alignment hole / no slice for this warp in this round
-      const int cell = hx & 0xffffff;
-      const unsigned se = (unsigned)hy;
-      const unsigned mask = n ? se >> 24 : 0u;
-      const int nx_item = (rd + 1) * nw + warp;   // next round's header in flight during this round
-      hx = 0;
-      if (nx_item < nslice) {
-        hx = __ldg(cl + ((nx_item << 5) | lane));
-        hy = __ldg(sl + ((nx_item << 5) | lane));
-      }
-      f32x2_t s[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s[k] = 0ull;
-      tri_walk(ra + (se & 0xffffff), rb + (se & 0xffffff), 0, (n + 1) >> 1, 2, 1, 32, dummy,
-               [&](const TriPair t) { tri_bwd_accumulate(t, gather(t.off0), gather(t.off1), s); });
-      float* pv = plane + cell;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float lo, hi;
-        upk2(s[k], lo, hi);
-        if ((mask >> k) & 1u) pv[off[k]] += lo + hi;
-        __syncthreads();
-      }
-      asm volatile("" : "+r"(hx), "+r"(hy));  // keep the prefetched header in plain registers until here
-    }
-  }
-  // ---- heavy cell pieces (and, for grids beyond shared memory, everything): whole warps take items from a shared
-  // counter; cell sums are added with atomics (8 per piece; global RED.ADD when the plane is not staged) ----
-  if (threadIdx.x == 0) next_item = phased ? nslice : 0;
-  __syncthreads();
+  // ---- walk: whole warps take work items from a shared counter: slices of 32 light cells (one thread per cell, the 8
+  // corner sums of its points built in registers), then pieces of heavy cells (one warp per piece).  Neighbouring cells
+  // share voxels, so a cell's sums must be ADDED to the plane with care.  A shared-memory float atomicAdd is a CAS loop
+  // whose 32 lanes are served one by one (ncu: ~30 wavefronts per warp instruction, two thirds of the kernel's
+  // shared-memory traffic).  Two forms, see `phases` below. ----
+  // phases == 0: light cells add their sums with shared-memory atomics (heavy pieces always do: 8 per piece).
+  // phases == 2 (pcfm_set_option("bwd_phases", 2)): a cell's 8 sums are parked in this CTA's own OUTPUT row (P floats of global memory that nothing
+  // reads until the plane is stored at the very end: room for P/8 cells) instead of being added with atomics; when all
+  // walks are done, every thread fetches the sums of up to kDeferCells cells and the CTA adds corner 0 of all cells,
+  // then corner 1, ...: cell -> cell + offset(k) is injective, so inside a phase no two threads touch the same voxel and
+  // the add is a plain load / add / store (8 barriers per row, perfectly balanced, and a voxel's light contributions
+  // arrive in a fixed order).  Slices beyond the room use atomics.  Measured at B=8, N=20000: no faster than the atomics
+  // (r=32: 0.141 vs 0.140 ms alone, 0.148 vs 0.137 inside the bench step; r=16: 0.154 vs 0.138) — the kernel is bound by
+  // the latency chain of its longest slice, not by the atomics' wavefronts; kept as an option for its fixed summation
+  // order.
+  // (Phases after every ROUND of statically dealt slices were measured too: the rounds walk in lock step, 0-15 % slower.)
+  constexpr int kDeferCells = 4;
+  const bool defer_ok = PLANE_SMEM && phases == 2 && ((((uintptr_t)o) & 15) == 0);
+  const int ndefer = defer_ok ? min(nslice, min(P >> 8, (int)(blockDim.x * kDeferCells) >> 5)) : 0;
   CellItem cur = next_cell_item(&next_item, nslice, nitem, cl, sl, hv);
   while (cur.item < nitem) {
     const CellItem nxt = next_cell_item(&next_item, nslice, nitem, cl, sl, hv);  // header in flight during this item
@@ -251,11 +215,21 @@ __global__ void __launch_bounds__(1024, 1)
       const int np = (n + 1) >> 1;
       tri_walk(ra + (se & 0xffffff), rb + (se & 0xffffff), 0, np, 2, 1, 32, dummy,
                [&](const TriPair t) { tri_bwd_accumulate(t, gather(t.off0), gather(t.off1), s); });
+      float sk[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float lo, hi;
         upk2(s[k], lo, hi);
-        if ((mask >> k) & 1u) atomicAdd(plane + cell + off[k], lo + hi);
+        sk[k] = lo + hi;
+      }
+      if (cur.item < ndefer) {   // deferred: the 8 sums of this cell wait in the (not yet written) output row
+        float4* sc = (float4*)o + 2 * ((cur.item << 5) | lane);
+        sc[0] = make_float4(sk[0], sk[1], sk[2], sk[3]);
+        sc[1] = make_float4(sk[4], sk[5], sk[6], sk[7]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if ((mask >> k) & 1u) atomicAdd(plane + cell + off[k], sk[k]);
       }
     } else {
       // Heavy cell piece: the whole warp, lanes stride the pair slots; the 8 partial sums are reduced by recursive
@@ -301,6 +275,33 @@ __global__ void __launch_bounds__(1024, 1)
   }
   if (!PLANE_SMEM) return;
   __syncthreads();
+  if (ndefer > 0) {   // uniform over the CTA
+    float dsum[kDeferCells][8];
+    int dcell[kDeferCells];
+    unsigned dmask[kDeferCells];
+#pragma unroll
+    for (int c = 0; c < kDeferCells; ++c) {
+      const int i = threadIdx.x + c * blockDim.x;
+      dmask[c] = 0u;
+      dcell[c] = 0;
+      if (i < (ndefer << 5)) {
+        const int hx = cl[i];
+        const int n = (int)((unsigned)hx >> 24);
+        dcell[c] = hx & 0xffffff;
+        dmask[c] = n ? (unsigned)sl[i] >> 24 : 0u;
+        const float4 u = __ldcg((const float4*)o + 2 * i), w = __ldcg((const float4*)o + 2 * i + 1);
+        dsum[c][0] = u.x; dsum[c][1] = u.y; dsum[c][2] = u.z; dsum[c][3] = u.w;
+        dsum[c][4] = w.x; dsum[c][5] = w.y; dsum[c][6] = w.z; dsum[c][7] = w.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+#pragma unroll
+      for (int c = 0; c < kDeferCells; ++c)
+        if ((dmask[c] >> k) & 1u) plane[dcell[c] + off[k]] += dsum[c][k];
+      __syncthreads();
+    }
+  }
   // ---- write the plane: one bulk (TMA) store when aligned, else a coalesced copy ----
   if ((((uintptr_t)o) & 15) == 0 && (P & 3) == 0 && use_tma) {
     fence_proxy_async();  // generic-proxy writes to `plane` -> visible to the async proxy
@@ -336,8 +337,6 @@ static int devox_bwd_cells(const float* grad_y, const float* coords, int b, int 
   int rc = reused ? cellplan_attach(true, b, n, t, &plan, &ws)
                   : cellplan_build(nullptr, coords, r, nullptr, b, n, t, nullptr, &plan, &ws, st);
   if (rc) return rc;
-  if ((g_opt_tri2 & 1) != 0 && plane_smem && tri2_bwd_ok(c, n, r))
-    return launch_tri2_bwd(grad_y, plan, grad_x, b, c, n, r, reused, st);
   dim3 grid(c, b);
   const bool row_smem = tri_bwd_smem(n, r, true, plane_smem) <= kTriSmemLimit;
   const size_t smem = tri_bwd_smem(n, r, row_smem, plane_smem);
@@ -347,13 +346,16 @@ static int devox_bwd_cells(const float* grad_y, const float* coords, int b, int 
   const int tma = (int)(g_opt_stage == 0);
   // a reused plan behind a memset must not start early (the kernel adds to the zeroed grid with global atomics)
   const bool dep = reused ? (g_opt_pdl >= 2 && plane_smem) : plan.pdl;
+  // light-cell adds: option bwd_phases = 0 -> shared-memory atomics (default: never slower), 2 = deferred conflict-free
+  // phases (fixed summation order of the light cells)
+  const int phases = g_opt_bwd_phases == 2 ? 2 : 0;
 #define PCFM_DBWD(RS, PS)                                                                                        \
   do {                                                                                                           \
     PCFM_CUDA(allow_dyn_smem((const void*)tri_bwd_kernel<RS, PS>, (int)kTriSmemLimit));                          \
     PCFM_CUDA(launch_dependent(tri_bwd_kernel<RS, PS>, grid, dim3(threads), smem, st, dep, grad_y, plan.cells,   \
                                plan.slot0, plan.meta, plan.heavy, (const float4*)plan.rec,                       \
                                (const float4*)plan.rec2, grad_x, c, n, r, plan.lcap, plan.hcap, plan.rcap, tma,  \
-                               (int)reused, g_opt_bwd_phases));                                                  \
+                               (int)reused, phases));                                                            \
   } while (0)
   if (plane_smem && row_smem) PCFM_DBWD(true, true);
   else if (plane_smem) PCFM_DBWD(false, true);
@@ -558,10 +560,7 @@ int pcfm_trilinear_devoxelize_forward_cells(const float* coords, const float* fe
   int rc = planned ? cellplan_attach(true, b, n, t, &plan, &ws)
                    : cellplan_build(nullptr, coords, r, nullptr, b, n, t, nullptr, &plan, &ws, st);
   if (rc) return rc;
-  if (c > 0 && (g_opt_tri2 == 1 || g_opt_tri2 == 2) && tri2_fwd_ok(c, n, r)) {
-    rc = launch_tri2_fwd(features, plan, outs, b, c, n, r, st);
-    if (rc) return rc;
-  } else if (c > 0) {
+  if (c > 0) {
     const size_t smem = tri_fwd_smem(n, r);
     const bool ps = (long long)r * r * r <= kTriFwdPlaneMax;
 #define PCFM_TFWD(RT, PS)                                                                                           \

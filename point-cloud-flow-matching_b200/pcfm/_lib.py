@@ -67,8 +67,6 @@ SIGNATURES = {
     "pcfm_chamfer3d_allpairs": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "pcfm_emd_allpairs_workspace": (_sz, [_i, _i, _i, _i]),
     "pcfm_emd_allpairs": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _sz, _p]),
-    "pcfm_chamfer3d_forward_host": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
-    "pcfm_avg_voxelize_forward_host": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

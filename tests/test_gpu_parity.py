@@ -245,14 +245,15 @@ def test_trilinear_devoxelize(be, oracle, ref, kw):
 @pytest.mark.parametrize("kw", [DEVOX_SHAPES[0], DEVOX_SHAPES[2], DEVOX_SHAPES[3], DEVOX_SHAPES[6], DEVOX_SHAPES[14]],
                          ids=lambda k: f"b{k['b']}c{k['c']}n{k['n']}r{k['res']}")
 def test_trilinear_walk_variants(be, oracle, kw):
-    """The optional walks (pcfm_set_option): tri2 = 1 two channels per persistent CTA (tri2.cu), bwd_phases = 1 light
-    cells added in 8 conflict-free corner phases instead of atomics — each against the oracle and the default kernels."""
+    """Devoxelize backward, how light cells reach the plane (pcfm_set_option("bwd_phases")): 0 = shared-memory atomics
+    (default), 2 = deferred conflict-free corner phases (sums parked in the output row; fixed summation order) — each
+    against the oracle and each other."""
     from pcfm import _lib
     coords, vox, gy, res = cases.devox_case(**kw)
     o_outs, o_inds, o_wgts = oracle.trilinear_devoxelize_forward(res, coords, vox)
     o_gx = oracle.trilinear_devoxelize_backward(gy, o_inds, o_wgts, res)
     got = {}
-    for name, opts in (("default", {}), ("tri2", {"tri2": 1}), ("bwd_phases", {"bwd_phases": 1})):
+    for name, opts in (("default", {}), ("bwd_deferred", {"bwd_phases": 2})):
         for k, v in opts.items():
             _lib.set_option(k, v)
         try:
@@ -268,13 +269,13 @@ def test_trilinear_walk_variants(be, oracle, kw):
         assert_close(host(gx), o_gx, f"grad_x ({name})", atol_frac=1e-5)
         assert_close(host(gx2), o_gx, f"grad_x, fresh plan ({name})", atol_frac=1e-5)
         got[name] = (host(outs), host(gx))
-    for name in ("tri2", "bwd_phases"):
+    for name in ("bwd_deferred",):
         assert_close(got[name][0], got["default"][0], f"outs: {name} vs default")
         assert_close(got[name][1], got["default"][1], f"grad_x: {name} vs default", atol_frac=1e-5)
-    # the phased backward adds a voxel's light contributions in a fixed order: bit-identical run to run when no heavy
+    # the deferred phases add a voxel's light contributions in a fixed order: bit-identical run to run when no heavy
     # cell (> 64 points, added with atomics) is involved
     if kw["n"] <= 2048:
-        _lib.set_option("bwd_phases", 1)
+        _lib.set_option("bwd_phases", 2)
         try:
             cc = cu(coords)
             a = host(be.pvcnn.trilinear_devoxelize_backward_coords(cu(gy), cc, res))
@@ -282,7 +283,7 @@ def test_trilinear_walk_variants(be, oracle, kw):
         finally:
             _lib.set_option("bwd_phases", 0)
         if int(np.bincount(np.floor(coords[0]).astype(np.int64).T.dot([res * res, res, 1])).max()) <= 64:
-            assert_equal(a, b, "phased backward, run to run")
+            assert_equal(a, b, "deferred-phase backward, run to run")
 
 
 def test_devox_backward_generic_is_deterministic(be):
