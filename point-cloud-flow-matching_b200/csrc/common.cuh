@@ -28,6 +28,8 @@ extern int g_opt_pdl;           // programmatic dependent launch: 0 = off, 1 = i
                                 // top, then releases the kernel behind it: launch + scheduling overlap the previous tail)
 extern int g_opt_fps;           // 0 = cluster FPS (points in registers) when the cloud fits, 1 = one CTA per cloud
 extern int g_opt_gather_bwd;    // 0 = gather backward with atomics (like the reference), 1 = sorted-segment sums
+extern int g_opt_grouping_bwd;  // 0 = grouping backward as a scatter into a shared-memory row when it fits (default), 1 = sorted-segment sums
+extern int g_opt_three_nn_bwd;  // the same choice for the 3-NN interpolate backward
 extern int g_opt_devox_fwd;     // 0 = devoxelize forward as a walk over the trilinear cell plan when the caller offers a
                                 // workspace (default), 1 = always the plane-staging point-lane kernels
 extern int g_opt_bwd_phases;    // devoxelize backward, how light cells reach the plane: 0 = shared-memory atomics (default),

@@ -293,6 +293,118 @@ __global__ void __launch_bounds__(256) devox_scatter_atomic_kernel(const float* 
   }
 }
 
+// Scatter-add of one row into a shared-memory row: the CTA zeroes grad_x[b, c, :] in shared memory, streams
+// grad_y[b, c, :] (E floats, coalesced) beside indices[b, :] (L2-resident: shared by the C rows of a cloud) and adds
+// every element to its target with a shared-memory atomic; the row leaves with one bulk (TMA) store.  No plan, no
+// memset, no global atomics (grouping.cu:36-58 issues one global atomicAdd per element).  Ball queries pad a
+// neighbourhood with copies of its first neighbour: runs of equal targets in consecutive lanes are summed in the warp
+// first (segmented suffix sum, 5 shuffles) so that a run costs one atomic instead of a CAS loop over its lanes.
+// Rows longer than one CTA's shared memory are cut into `tiles` slices of `slice` floats, one CTA each: grid
+// (C * tiles, B); every CTA of a row streams all E elements and keeps the ones that land in its slice.  (Dealing the
+// elements to the CTAs of a cluster instead, with the adds going to the owner through distributed shared memory, was
+// measured 7x slower: 13.8 ms against 1.9 ms at N = 100000 — remote float atomics are generic-address CAS loops.)
+constexpr int kScatterUnroll = 16;
+// WEIGHTED (3-NN interpolate backward, interpolate.cu:158-181): element e carries weight wgt[b, e] and the source value
+// grad_y[b, c, e % S] (E = 3 * S: the three neighbours of every point); product and sum are rounded separately, as the
+// reference's atomicAdd(grad_x + idx, grad_y * weight) does.
+template <int THREADS, bool TILED, bool WEIGHTED>
+__global__ void __launch_bounds__(THREADS, THREADS == 512 ? 2 : 1)
+    row_scatter_kernel(const float* __restrict__ grad_y, const int* __restrict__ indices, const float* __restrict__ wgt,
+                       float* __restrict__ grad_x, int C, int S, int T, int E, int tiles, int slice, int use_tma) {
+  extern __shared__ __align__(128) float smem[];
+  const int c = TILED ? blockIdx.x / tiles : blockIdx.x, tile = TILED ? blockIdx.x - c * tiles : 0, b = blockIdx.y;
+  const float* src = grad_y + ((long long)b * C + c) * S;
+  const int* idx = indices + (long long)b * E;
+  const float* wv = WEIGHTED ? wgt + (long long)b * E : nullptr;
+  const int t0 = tile * slice, count = max(0, min(slice, T - t0));  // this CTA's part of the row
+  float* o = grad_x + ((long long)b * C + c) * T + t0;
+  for (int i = threadIdx.x; i < (slice >> 2); i += THREADS) ((float4*)smem)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  constexpr int kStep = 32 * kScatterUnroll, kWarps = THREADS >> 5;
+  const bool few_wraps = (long long)E <= 3LL * S;
+  for (int base = warp * kStep; base < E; base += kWarps * kStep) {
+    int t[kScatterUnroll];
+    float v[kScatterUnroll];
+#pragma unroll
+    for (int k = 0; k < kScatterUnroll; ++k) {  // all loads of the step in flight before the first is used
+      const int e = base + k * 32 + lane;
+      t[k] = e < E ? __ldg(idx + e) - t0 : -1;
+      if (WEIGHTED) {
+        int si = e;  // e % S without a division for the 3-NN shape (E = 3 * S)
+        if (few_wraps) {
+          if (si >= S) si -= S;
+          if (si >= S) si -= S;
+        } else {
+          si = e % S;
+        }
+        v[k] = e < E ? __fmul_rn(__ldg(wv + e), __ldg(src + si)) : 0.f;
+      }
+      else v[k] = e < E ? (TILED ? __ldg(src + e) : __ldcs(src + e)) : 0.f;  // one pass: streaming, evict first
+    }
+#pragma unroll
+    for (int k = 0; k < kScatterUnroll; ++k) {
+      const int prev = __shfl_up_sync(0xffffffffu, t[k], 1);
+      const bool head = lane == 0 || t[k] != prev;
+      const unsigned heads = __ballot_sync(0xffffffffu, head);
+      float x = v[k];
+      if (heads != 0xffffffffu) {  // warp-uniform: some run is longer than one lane
+        const unsigned above = lane == 31 ? 0u : heads & (0xffffffffu << (lane + 1));
+        const int end = above ? __ffs(above) - 1 : 32;  // this lane's run ends before lane `end`
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const float y = __shfl_down_sync(0xffffffffu, x, d);
+          if (lane + d < end) x += y;
+        }
+      }
+      if (head && (unsigned)t[k] < (unsigned)count) atomicAdd(smem + t[k], x);
+    }
+  }
+  __syncthreads();
+  if (use_tma && (((uintptr_t)o) & 15) == 0 && (count & 3) == 0 && count > 0) {
+    fence_proxy_async();  // generic-proxy writes to the row -> visible to the async proxy
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (uint32_t off = 0; off < (uint32_t)count * 4u; off += kBulkChunk)
+        bulk_s2g((char*)o + off, (const char*)smem + off, min(kBulkChunk, (uint32_t)count * 4u - off));
+      bulk_commit();
+      bulk_wait_read();
+    }
+  } else {
+    for (int i = threadIdx.x; i < count; i += THREADS) o[i] = smem[i];
+  }
+}
+
+constexpr int kScatterTwoCtaFloats = 28672;  // 112 KB: two CTAs per SM
+constexpr int kScatterMaxTiles = 8;          // beyond 8 slices of 28672 points the sorted-segment path takes over
+static bool scatter_rows_fits(long long t) { return t <= (long long)kScatterMaxTiles * kScatterTwoCtaFloats; }
+// s = length of a source row (e for the unit form, where element e reads grad_y[b, c, e])
+static int scatter_rows_smem(const float* grad_y, const int* indices, const float* wgt, int b, int c, int s, int t, int e,
+                             float* grad_x, cudaStream_t st) {
+  const int tiles = t <= kMaxStageFloats ? 1 : cdiv(t, kScatterTwoCtaFloats);
+  const int slice = (cdiv(t, tiles) + 3) & ~3;
+  const size_t smem = (size_t)slice * sizeof(float);
+  const int tma = (int)(g_opt_stage == 0);
+  dim3 grid(c * tiles, b);
+#define PCFM_SCAT(TH, TI, WE)                                                                                        \
+  do {                                                                                                               \
+    PCFM_CUDA(allow_dyn_smem((const void*)row_scatter_kernel<TH, TI, WE>, (int)(kMaxStageFloats * sizeof(float))));  \
+    row_scatter_kernel<TH, TI, WE><<<grid, TH, smem, st>>>(grad_y, indices, wgt, grad_x, c, s, t, e, tiles, slice,   \
+                                                           tma);                                                     \
+  } while (0)
+#define PCFM_SCAT_W(TH, TI) \
+  do {                      \
+    if (wgt) PCFM_SCAT(TH, TI, true); else PCFM_SCAT(TH, TI, false); \
+  } while (0)
+  if (tiles > 1) PCFM_SCAT_W(512, true);
+  else if (slice <= kScatterTwoCtaFloats) PCFM_SCAT_W(512, false);
+  else PCFM_SCAT_W(1024, false);
+#undef PCFM_SCAT_W
+#undef PCFM_SCAT
+  PCFM_LAUNCHED();
+  return 0;
+}
+
 }  // namespace pcfm
 
 using namespace pcfm;
@@ -437,6 +549,10 @@ int pcfm_grouping_backward(const float* grad_y, const int* indices, int b, int c
   if (b < 0 || c < 0 || n < 0 || m < 0 || u < 0 || (long long)m * u > 0x7fffffffLL) return PCFM_E_BADARG;
   if (b == 0 || c == 0 || n == 0) return 0;
   if (!grad_x || ((long long)m * u > 0 && (!grad_y || !indices))) return PCFM_E_BADARG;
+  // rows of up to 229376 points: scatter into shared-memory rows (option "grouping_bwd" = 1: sorted-segment sums, whose
+  // result does not depend on the scheduling order — and which any longer row takes)
+  if (g_opt_grouping_bwd == 0 && scatter_rows_fits(n) && b <= 65535 && (long long)c * kScatterMaxTiles <= 0x7fffffffLL)
+    return scatter_rows_smem(grad_y, indices, nullptr, b, c, m * u, n, m * u, grad_x, (cudaStream_t)stream);
   return scatter_unit(grad_y, indices, b, c, n, m * u, grad_x, workspace, workspace_bytes,
                       (cudaStream_t)stream);
 }
@@ -492,6 +608,9 @@ int pcfm_three_nn_interpolate_backward(const float* grad_y, const int* idx, cons
   if (b == 0 || c == 0 || m == 0) return 0;
   if (!grad_x || (n > 0 && (!grad_y || !idx || !wgt))) return PCFM_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
+  // the m centres of a row fit in shared memory: scatter (option "three_nn_bwd" = 1: sorted-segment sums)
+  if (g_opt_three_nn_bwd == 0 && n > 0 && scatter_rows_fits(m) && b <= 65535 && (long long)c * kScatterMaxTiles <= 0x7fffffffLL)
+    return scatter_rows_smem(grad_y, idx, wgt, b, c, n, m, 3 * n, grad_x, st);
   Workspace ws(workspace, workspace_bytes);
   int* cnt = ws.take<int>((size_t)b * m);
   if (!ws.ok()) return PCFM_E_WORKSPACE;

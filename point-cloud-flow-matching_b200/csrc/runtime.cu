@@ -18,6 +18,8 @@ int g_opt_bwd_phases = 0;
 int g_opt_emd_cluster = 1;
 int g_opt_chamfer_once = 1;
 int g_opt_gather_bwd = 0;
+int g_opt_grouping_bwd = 0;
+int g_opt_three_nn_bwd = 0;
 int g_opt_fps = 0;
 int g_opt_pdl = 2;
 int g_opt_devox_il = 1;
@@ -81,6 +83,8 @@ int pcfm_set_option(const char* key, int value) {
   if (!strcmp(key, "pdl")) { pcfm::g_opt_pdl = value; return 0; }
   if (!strcmp(key, "fps")) { pcfm::g_opt_fps = value; return 0; }
   if (!strcmp(key, "gather_bwd")) { pcfm::g_opt_gather_bwd = value; return 0; }
+  if (!strcmp(key, "grouping_bwd")) { pcfm::g_opt_grouping_bwd = value; return 0; }
+  if (!strcmp(key, "three_nn_bwd")) { pcfm::g_opt_three_nn_bwd = value; return 0; }
   if (!strcmp(key, "plan")) { pcfm::g_opt_plan = value; return 0; }
   if (!strcmp(key, "devox_fwd")) { pcfm::g_opt_devox_fwd = value; return 0; }
   if (!strcmp(key, "bwd_phases")) { pcfm::g_opt_bwd_phases = value; return 0; }

@@ -210,6 +210,8 @@ def main():
                                  (lambda: R.three_nearest_neighbors_interpolate_backward(gint, i3, w3, m)) if R else None),
             }
             for op, (fn, rfn) in cases.items():
+                if args.ops and op not in args.ops.split(","):
+                    continue
                 it = 2 if op == "fps" else args.iters
                 row = {"op": op, "B": b, "N": n, "M": m, "U": u, "C": c, "ms": round(timeit(fn, iters=it, warm=1), 4)}
                 if op == "fps":

@@ -413,6 +413,32 @@ def test_fps_cluster_and_single_cta_kernels_pick_the_reference_winners(be, oracl
         _lib.set_option("fps", 0)
 
 
+@pytest.mark.parametrize("b,c,n,m,u,kind", [(2, 5, 1000, 250, 32, "padded"), (1, 3, 4099, 300, 7, "random"),
+                                            (2, 4, 20000, 1250, 32, "padded"), (1, 2, 30001, 100, 64, "padded"),
+                                            (1, 2, 60000, 50, 16, "random"), (2, 3, 100000, 2000, 32, "padded"),
+                                            (1, 1, 300001, 100, 8, "random"), (1, 1, 9, 1, 1, "random")])
+def test_grouping_backward_forms(be, oracle, b, c, n, m, u, kind):
+    """grouping backward as a scatter into a shared-memory row (default; rows beyond 55296 points are cut into slices
+    with one CTA each, beyond 229376 points the sorted-segment path takes over) and as sorted-segment sums (pcfm_set_option("grouping_bwd", 1)) against the oracle.  "padded": neighbourhoods
+    filled up with copies of their first neighbour, as the ball query leaves them (runs of equal targets)."""
+    from pcfm import _lib
+    g = rng(900 + n + u)
+    idx = g.integers(0, n, size=(b, m, u)).astype(np.int32)
+    if kind == "padded":
+        found = g.integers(1, u + 1, size=(b, m))
+        idx = np.where(np.arange(u)[None, None, :] < found[..., None], idx, idx[..., :1]).astype(np.int32)
+    gy = g.standard_normal((b, c, m, u)).astype(np.float32)
+    want = oracle.grouping_backward(gy, idx, n)
+    for opt in (0, 1):
+        _lib.set_option("grouping_bwd", opt)
+        try:
+            got = host(be.pvcnn.grouping_backward(cu(gy), cu(idx), n))
+        finally:
+            _lib.set_option("grouping_bwd", 0)
+        assert_close(got, want, f"grouping backward (grouping_bwd={opt})", atol_frac=1e-6)
+        assert_equal(got != 0, want != 0, f"sparsity pattern (grouping_bwd={opt})")
+
+
 @pytest.mark.parametrize("kw", PN_SHAPES, ids=lambda k: f"{k['kind']}n{k['n']}m{k['m']}")
 def test_fps_ballquery_grouping_gather_3nn(be, oracle, ref, kw):
     pts, feat, cfeat = cases.pointnet_case(**kw)
@@ -453,6 +479,12 @@ def test_fps_ballquery_grouping_gather_3nn(be, oracle, ref, kw):
     assert_close(host(o3), oo3, "3nn interpolate")
     g3 = be.pvcnn.three_nearest_neighbors_interpolate_backward(cu(feat), i3, w3, m)
     assert_close(host(g3), oracle.three_nn_interpolate_backward(feat, oi3, ow3, m), "3nn backward")
+    _lib.set_option("three_nn_bwd", 1)     # sorted-segment sums instead of the shared-memory scatter
+    try:
+        g3s = be.pvcnn.three_nearest_neighbors_interpolate_backward(cu(feat), i3, w3, m)
+    finally:
+        _lib.set_option("three_nn_bwd", 0)
+    assert_close(host(g3s), oracle.three_nn_interpolate_backward(feat, oi3, ow3, m), "3nn backward (sorted segments)")
     if ref["pvcnn"] is not None:
         R = ref["pvcnn"]
         assert_equal(host(fidx), host(R.furthest_point_sampling(cu(pts), m)), "fps vs reference")
