@@ -323,7 +323,7 @@ def dp_training_step(torch, dist, dev, rank, world, barrier, max_over_ranks, _li
            "per_gpu_batch": B, "points": NPTS, "parameters": nparam,
            "grad_allreduce_bytes_per_step": nparam * 4 if world > 1 else 0,
            "ms_per_step": ms, "mpts_per_s": B * NPTS * world / ms / 1e3, "scaling": "weak",
-           "pcfm_launches_per_step": _lib.launch_count() / steps, "loss": float(loss), "steps": steps}
+           "pcfm_launches_per_step": _lib.launch_count() / steps, "loss": float(loss.detach()), "steps": steps}
     del model, net, opt
     return out
 
