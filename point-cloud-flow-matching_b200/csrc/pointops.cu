@@ -82,6 +82,15 @@ __device__ __forceinline__ int fps_key_index(unsigned long long key) {
   return (int)(((0x3FFFFFu - (lo & 0x3FFFFFu)) << 9) | (511u - (lo >> 22)));
 }
 
+// warp maximum of 64-bit keys with two REDUX.MAX (high words, then the low words of the lanes that hold the maximum)
+// instead of five 64-bit shuffle steps
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
 template <bool SMEM>
 __global__ void __launch_bounds__(1024, 1)
     fps_kernel(const float* __restrict__ coords, int n, int m, float* __restrict__ dist_g,
@@ -128,20 +137,11 @@ __global__ void __launch_bounds__(1024, 1)
       const unsigned long long key = fps_key(d2, k);
       best = key > best ? key : best;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
-      best = other > best ? other : best;
-    }
+    best = warp_max_u64(best);
     if (lane == 0) wbest[wid] = best;
     __syncthreads();
     if (wid == 0) {
-      unsigned long long v = lane < nw ? wbest[lane] : 0ull;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-        v = other > v ? other : v;
-      }
+      const unsigned long long v = warp_max_u64(lane < nw ? wbest[lane] : 0ull);
       if (lane == 0) {
         const int w = v ? fps_key_index(v) : 0;
         s_old = w;
@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(1024, 1)
 // round trip.  Same 64-bit key => same winners as the one-CTA kernel and the reference.
 // -------------------------------------------------------------------------------------------------
 constexpr int kFpsCl = 8;
+constexpr int kFpsClusterMin = 3072;  // measured crossover (B = 8, M = N / 4): 2048 points equal, 4096 points 1.44x for the cluster
 struct __align__(16) FpsSlot {
   unsigned long long key;
   float x, y, z;
@@ -169,13 +170,20 @@ struct __align__(16) FpsSlot {
 
 // XYZ_SMEM (clouds of 65537..131072 points, 16 points per thread): the coordinates live in shared memory
 // ([3][points of this CTA], conflict-free strided reads), only the running distances stay in registers.
-template <int PPT, bool XYZ_SMEM>
+// PUSH: instead of publishing the slot locally and meeting at a cluster barrier (arrive + wait, then a remote read: two
+// cluster round trips per round), the winner's warp WRITES the slot into the inbox of all 8 CTAs with st.async, whose
+// completion is counted by an mbarrier in the receiving CTA (complete_tx): one one-way trip per round, and the slots are
+// read from local shared memory.  Inboxes and barriers are double-buffered by round parity: a CTA can only be sent the
+// slots of round j + 2 after it has itself sent round j + 1, i.e. after all its warps have consumed round j.
+template <int PPT, bool XYZ_SMEM, bool PUSH>
 __global__ void __cluster_dims__(kFpsCl, 1, 1) __launch_bounds__(1024, 1)
     fps_cluster_kernel(const float* __restrict__ coords, int n, int m, int* __restrict__ indices) {
   cg::cluster_group cluster = cg::this_cluster();
   extern __shared__ __align__(16) float sxyz[];  // XYZ_SMEM: x[per] y[per] z[per]
   __shared__ unsigned long long wbest[32];
   __shared__ FpsSlot slot[2];
+  __shared__ FpsSlot inbox[2][kFpsCl];
+  __shared__ uint64_t inbar[2];
   if (m <= 0) return;
   const int q = (int)cluster.block_rank(), b = blockIdx.x / kFpsCl;
   const float* cb = coords + (long long)b * 3 * n;
@@ -197,8 +205,17 @@ __global__ void __cluster_dims__(kFpsCl, 1, 1) __launch_bounds__(1024, 1)
   }
   if (XYZ_SMEM) __syncthreads();
   if (q == 0 && tid == 0) ib[0] = 0;
+  if (PUSH) {
+    if (tid == 0) {
+      mbar_init(&inbar[0], 1);
+      mbar_init(&inbar[1], 1);
+      fence_mbar_init();
+    }
+    cluster.sync();  // nobody sends before every barrier of the cluster exists
+  }
   float x1 = cb[0], y1 = cb[n], z1 = cb[2LL * n];  // the first centre is point 0
   for (int j = 1; j < m; ++j) {
+    if (PUSH && tid == 0) mbar_arrive_expect_tx(&inbar[j & 1], kFpsCl * 24u);  // 8 slots of 24 bytes will arrive
     unsigned long long best = 0ull;  // below every real key (distances are >= 0)
     float bx = 0.f, by = 0.f, bz = 0.f;
 #pragma unroll
@@ -216,50 +233,66 @@ __global__ void __cluster_dims__(kFpsCl, 1, 1) __launch_bounds__(1024, 1)
       const unsigned long long key = k < k_hi ? fps_key(d2, k) : 0ull;
       if (key > best) { best = key; bx = x; by = y; bz = z; }
     }
-    unsigned long long v = best;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-      v = other > v ? other : v;
-    }
+    unsigned long long v = warp_max_u64(best);
     if (lane == 0) wbest[wid] = v;
     __syncthreads();
-    v = lane < nw ? wbest[lane] : 0ull;  // every warp reduces the warp results itself: one barrier, no broadcast
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const unsigned long long other = __shfl_xor_sync(0xffffffffu, v, o);
-      v = other > v ? other : v;
-    }
-    FpsSlot* mine = &slot[j & 1];
-    if (v == 0ull) {
-      if (tid == 0) { mine->key = 0ull; mine->x = 0.f; mine->y = 0.f; mine->z = 0.f; }  // this CTA owns no point
-    } else if (best == v) {  // keys are unique per point: exactly one thread
-      mine->key = v; mine->x = bx; mine->y = by; mine->z = bz;
-    }
-    cluster.sync();
-    // lanes 0..7 of every warp fetch one CTA's slot each, 3 shuffle steps pick the cluster-wide winner
+    v = warp_max_u64(lane < nw ? wbest[lane] : 0ull);  // every warp reduces the warp results itself: one barrier, no broadcast
     unsigned long long ck = 0ull;
     float cx = 0.f, cy = 0.f, cz = 0.f;
-    if (lane < kFpsCl) {
-      const FpsSlot* rs = cluster.map_shared_rank(mine, lane);
-      const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rs);            // key, (x, y)
-      const float2 zz = *reinterpret_cast<const float2*>(&rs->z);                // z, pad
-      ck = a.x;
-      cx = __uint_as_float((unsigned)a.y);
-      cy = __uint_as_float((unsigned)(a.y >> 32));
-      cz = zz.x;
+    if (PUSH) {
+      // the warp of the winning thread (warp 0 if this CTA owns no point: key 0) sends the slot to the 8 inboxes
+      const unsigned who = __ballot_sync(0xffffffffu, v != 0ull && best == v);  // keys are unique: at most one lane
+      if (v != 0ull ? who != 0u : wid == 0) {
+        const int src = who ? __ffs(who) - 1 : 0;
+        const float sx = v ? __shfl_sync(0xffffffffu, bx, src) : 0.f, sy = v ? __shfl_sync(0xffffffffu, by, src) : 0.f,
+                    sz = v ? __shfl_sync(0xffffffffu, bz, src) : 0.f;
+        if (lane < kFpsCl) {
+          uint32_t dst, rbar;
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(dst) : "r"(smem_u32(&inbox[j & 1][q])), "r"(lane));
+          asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(smem_u32(&inbar[j & 1])), "r"(lane));
+          const unsigned long long xy = ((unsigned long long)__float_as_uint(sy) << 32) | __float_as_uint(sx);
+          const unsigned long long zp = (unsigned long long)__float_as_uint(sz);
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+                       ::"r"(dst), "l"(v), "l"(xy), "r"(rbar) : "memory");
+          asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+                       ::"r"(dst + 16u), "l"(zp), "r"(rbar) : "memory");
+        }
+      }
+      mbar_wait(&inbar[j & 1], (uint32_t)((j - 1) >> 1) & 1u);  // all 8 slots of this round have landed here (rounds start at 1)
+      if (lane < kFpsCl) {
+        const FpsSlot* rs = &inbox[j & 1][lane];
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rs);    // key, (x, y)
+        ck = a.x;
+        cx = __uint_as_float((unsigned)a.y);
+        cy = __uint_as_float((unsigned)(a.y >> 32));
+        cz = rs->z;
+      }
+    } else {
+      FpsSlot* mine = &slot[j & 1];
+      if (v == 0ull) {
+        if (tid == 0) { mine->key = 0ull; mine->x = 0.f; mine->y = 0.f; mine->z = 0.f; }  // this CTA owns no point
+      } else if (best == v) {  // keys are unique per point: exactly one thread
+        mine->key = v; mine->x = bx; mine->y = by; mine->z = bz;
+      }
+      cluster.sync();
+      // lanes 0..7 of every warp fetch one CTA's slot each, 3 shuffle steps pick the cluster-wide winner
+      if (lane < kFpsCl) {
+        const FpsSlot* rs = cluster.map_shared_rank(mine, lane);
+        const ulonglong2 a = *reinterpret_cast<const ulonglong2*>(rs);            // key, (x, y)
+        const float2 zz = *reinterpret_cast<const float2*>(&rs->z);                // z, pad
+        ck = a.x;
+        cx = __uint_as_float((unsigned)a.y);
+        cy = __uint_as_float((unsigned)(a.y >> 32));
+        cz = zz.x;
+      }
     }
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-      const unsigned long long ok = __shfl_xor_sync(0xffffffffu, ck, o);
-      const float ox = __shfl_xor_sync(0xffffffffu, cx, o), oy = __shfl_xor_sync(0xffffffffu, cy, o),
-                  oz = __shfl_xor_sync(0xffffffffu, cz, o);
-      if (ok > ck) { ck = ok; cx = ox; cy = oy; cz = oz; }
-    }
-    ck = __shfl_sync(0xffffffffu, ck, 0);
-    x1 = __shfl_sync(0xffffffffu, cx, 0);
-    y1 = __shfl_sync(0xffffffffu, cy, 0);
-    z1 = __shfl_sync(0xffffffffu, cz, 0);
+    // the cluster-wide winner among the 8 slots (lanes >= 8 hold key 0) and the lane that holds it
+    const unsigned long long win = warp_max_u64(ck);
+    const int wl = __ffs(__ballot_sync(0xffffffffu, ck == win)) - 1;
+    ck = win;
+    x1 = __shfl_sync(0xffffffffu, cx, wl);
+    y1 = __shfl_sync(0xffffffffu, cy, wl);
+    z1 = __shfl_sync(0xffffffffu, cz, wl);
     if (ck == 0ull) { x1 = cb[0]; y1 = cb[n]; z1 = cb[2LL * n]; }  // degenerate (all distances 0 at index 0): index 0
     if (q == 0 && tid == 0) ib[j] = ck ? fps_key_index(ck) : 0;
   }
@@ -408,26 +441,41 @@ int pcfm_furthest_point_sampling(const float* coords, int b, int n, int m, int* 
   if (b == 0 || m == 0) return 0;
   if (!coords || !indices || n == 0) return PCFM_E_BADARG;
   cudaStream_t st = (cudaStream_t)stream;
-  // Cluster kernel from 6144 points up (below, its ~1.4 us cluster barrier per round loses to the one-CTA kernel):
+  // Cluster kernel from 3072 points up (below, the ~0.55 us exchange per round loses to the one-CTA kernel):
   // points in registers (<= 8 per thread) up to 65536 points, coordinates in shared memory up to 131072.
-  if (g_opt_fps == 0 && n >= 6144 && n <= kFpsCl * 1024 * 16) {
+  // option "fps": 0 = cluster kernel, slots pushed into the peers' inboxes (default), 2 = cluster kernel with a cluster
+  // barrier per round, 1 = always one CTA per cloud
+  if (g_opt_fps != 1 && n >= kFpsClusterMin && n <= kFpsCl * 1024 * 16) {
+    const bool push = g_opt_fps == 0;
     const int per = cdiv(n, kFpsCl);
     dim3 grid(b * kFpsCl);
     if (per > 1024 * 8) {
       const size_t smem = (size_t)per * 3 * sizeof(float);
-      PCFM_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      PCFM_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<16, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      16384 * 3 * (int)sizeof(float)));
-      fps_cluster_kernel<16, true><<<grid, 1024, smem, st>>>(coords, n, m, indices);
+      PCFM_CUDA(cudaFuncSetAttribute(fps_cluster_kernel<16, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     16384 * 3 * (int)sizeof(float)));
+      if (push) fps_cluster_kernel<16, true, true><<<grid, 1024, smem, st>>>(coords, n, m, indices);
+      else fps_cluster_kernel<16, true, false><<<grid, 1024, smem, st>>>(coords, n, m, indices);
     } else {
-      int nt = 512, ppt = 1;
-      while (ppt < 8 && nt * ppt < per) ppt *= 2;
-      if (nt * ppt < per) nt = 1024;
+      const int nt = cdiv(per, 512) <= 8 ? 512 : 1024;
+      const int ppt = cdiv(per, nt);  // 1..8 points per thread, no padded work beyond the last thread's
+#define PCFM_FPS(P)                                                                                  \
+  do {                                                                                               \
+    if (push) fps_cluster_kernel<P, false, true><<<grid, nt, 0, st>>>(coords, n, m, indices);        \
+    else fps_cluster_kernel<P, false, false><<<grid, nt, 0, st>>>(coords, n, m, indices);            \
+  } while (0)
       switch (ppt) {
-        case 1: fps_cluster_kernel<1, false><<<grid, nt, 0, st>>>(coords, n, m, indices); break;
-        case 2: fps_cluster_kernel<2, false><<<grid, nt, 0, st>>>(coords, n, m, indices); break;
-        case 4: fps_cluster_kernel<4, false><<<grid, nt, 0, st>>>(coords, n, m, indices); break;
-        default: fps_cluster_kernel<8, false><<<grid, nt, 0, st>>>(coords, n, m, indices); break;
+        case 1: PCFM_FPS(1); break;
+        case 2: PCFM_FPS(2); break;
+        case 3: PCFM_FPS(3); break;
+        case 4: PCFM_FPS(4); break;
+        case 5: PCFM_FPS(5); break;
+        case 6: PCFM_FPS(6); break;
+        case 7: PCFM_FPS(7); break;
+        default: PCFM_FPS(8); break;
       }
+#undef PCFM_FPS
     }
     PCFM_LAUNCHED();
     return 0;

@@ -396,21 +396,24 @@ PN_SHAPES = [
 ]
 
 
-@pytest.mark.parametrize("n,m,kind", [(600, 150, "lattice"), (3000, 700, "rand"), (9, 9, "rand"), (6144, 300, "lattice"),
+@pytest.mark.parametrize("n,m,kind", [(600, 150, "lattice"), (3000, 700, "rand"), (9, 9, "rand"), (3072, 300, "lattice"),
+                                      (4100, 500, "rand"), (6144, 300, "lattice"), (20000, 700, "rand"),
                                       (40000, 64, "rand"), (70000, 40, "rand"), (131073, 12, "rand")])
 def test_fps_cluster_and_single_cta_kernels_pick_the_reference_winners(be, oracle, n, m, kind):
-    """All FPS kernels (one CTA per cloud below 6144 and above 131072 points; 8-CTA cluster with the points in registers
-    up to 65536 points, coordinates in shared memory up to 131072) must reproduce the reference's choice in every
-    round, including its tie-break on lattice clouds."""
+    """All FPS kernels (one CTA per cloud below 3072 and above 131072 points; 8-CTA cluster with 1..8 points per thread
+    in registers up to 65536 points, coordinates in shared memory up to 131072; slots exchanged by st.async pushes
+    or, option "fps" = 2, by a cluster barrier and remote reads) must reproduce the reference's choice in every round,
+    including its tie-break on lattice clouds."""
     from pcfm import _lib
     pts, _, _ = cases.pointnet_case(seed=45 + n % 7, b=2, c=1, n=n, m=m, kind=kind)
     want = oracle.furthest_point_sampling(pts, m)
     assert_equal(host(be.pvcnn.furthest_point_sampling(cu(pts), m)), want, "fps (default kernel)")
-    _lib.set_option("fps", 1)
-    try:
-        assert_equal(host(be.pvcnn.furthest_point_sampling(cu(pts), m)), want, "fps (one CTA per cloud)")
-    finally:
-        _lib.set_option("fps", 0)
+    for opt, what in ((1, "one CTA per cloud"), (2, "cluster kernel with a cluster barrier per round")):
+        _lib.set_option("fps", opt)
+        try:
+            assert_equal(host(be.pvcnn.furthest_point_sampling(cu(pts), m)), want, f"fps ({what})")
+        finally:
+            _lib.set_option("fps", 0)
 
 
 @pytest.mark.parametrize("b,c,n,m,u,kind", [(2, 5, 1000, 250, 32, "padded"), (1, 3, 4099, 300, 7, "random"),

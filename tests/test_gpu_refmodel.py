@@ -138,6 +138,31 @@ def test_inference_mode_forward(models):
     assert err <= 1e-5, f"inference_mode output differs: {err:.3e}"
 
 
+def test_training_step_under_autocast(models):
+    """train.py:620 runs the loss under torch.autocast (--amp / --use_bf16); models.py:513 switches autocast off around
+    the PVConv stages, so the primitives must see fp32 tensors (they raise on anything else) while the velocity head
+    runs in bf16."""
+    dev = torch.device("cuda")
+    net = refmodel.make_hybrid(dev).train()
+    x, t, cond = _inputs(2, 2048, dev, seed=11)
+    z = torch.randn_like(x)
+    xt = (1 - t)[:, None, None] * z + t[:, None, None] * x
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        v = net(xt, t, cond)
+        loss = torch.nn.functional.mse_loss(v.float(), x - z)
+    loss.backward()
+    assert torch.isfinite(loss)
+    from pcfm.nn import PVConv
+    for m in net.modules():
+        if isinstance(m, PVConv):
+            g = m.voxel_layers[0].weight.grad
+            assert g is not None and g.dtype == torch.float32 and torch.isfinite(g).all() and g.abs().sum() > 0
+    with torch.no_grad():
+        v32 = net(xt, t, cond)
+    err = (v.float() - v32).abs().max().item() / max(v32.abs().max().item(), 1e-30)
+    assert err <= 1e-1, f"bf16 autocast output is far from the fp32 one: {err:.3e}"
+
+
 def test_hybridmlp_matches_the_reference_extension(models):
     """Same model, same weights, same inputs: the compiled reference `_pvcnn_backend` (oracle/_ref) against this
     library under the reference's models.py, forward and backward."""
