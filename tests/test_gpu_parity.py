@@ -387,6 +387,54 @@ def test_pvconv_chain_at_the_bench_shapes_against_the_reference_kernels(be, ref,
     print(f"bench shape C={c} r={res}: " + ", ".join(f"{k} {a:.1e} (ref vs ref {e:.1e})" for k, (a, e) in report.items()))
 
 
+@pytest.mark.parametrize("c,res", [(128, 32), (256, 16), (256, 8)], ids=lambda v: str(v))
+def test_pvconv_primitives_are_adjoint_pairs_at_the_bench_shapes(be, c, res):
+    """Size-independent property at BASELINE config 2 (B=8, N=20000): each backward is the ADJOINT of its linear forward,
+    <forward(x), y> = <x, backward(y)> for random x, y (inner products in float64), and both forwards are linear.  Needs
+    no oracle and no reference, so it holds the full-size kernels to account on any box."""
+    b, n = 8, 20000
+    g = torch.Generator(device="cuda").manual_seed(2000 + res)
+    coords = torch.randn(b, 3, n, device="cuda", generator=g)
+    nc = coords - coords.mean(2, keepdim=True)
+    nc = nc / (nc.norm(dim=1, keepdim=True).max(dim=2, keepdim=True).values * 2.0 + 1e-6) + 0.5
+    nc = torch.clamp(nc * res, 0, res - 1).contiguous()
+    vox = torch.round(nc).to(torch.int32).contiguous()
+    feat = torch.randn(b, c, n, device="cuda", generator=g)
+    feat2 = torch.randn(b, c, n, device="cuda", generator=g)
+    grid = torch.randn(b, c, res ** 3, device="cuda", generator=g)
+    gy = torch.randn(b, c, n, device="cuda", generator=g)
+    P = be.pvcnn
+
+    def dot(x, y):
+        return float((x.double() * y.double()).sum())
+
+    def norm(x):
+        return float(x.double().square().sum().sqrt())
+
+    # avg_voxelize: forward F -> V (mean per voxel), backward V -> F
+    out, ind, cnt = P.avg_voxelize_forward(feat, vox, res, nc)
+    back = P.avg_voxelize_backward(grid, ind, cnt)
+    # (the inner products of random fields are sums of ~1e7 signed terms: the identity is held relative to the product
+    # of the norms, Cauchy-Schwarz's bound on either side)
+    lhs, rhs = dot(out, grid), dot(feat, back)
+    assert abs(lhs - rhs) <= 1e-6 * norm(out) * norm(grid), f"avg_voxelize adjoint identity: {lhs} vs {rhs}"
+    out2 = P.avg_voxelize_forward(feat2, vox, res, nc)[0]
+    out12 = P.avg_voxelize_forward(feat + 0.5 * feat2, vox, res, nc)[0]
+    err = float((out12 - (out + 0.5 * out2)).abs().max() / out12.abs().max())
+    assert err <= 1e-5, f"avg_voxelize linearity: {err:.2e}"
+    assert int(cnt.sum()) == b * n, "every point is counted once"
+    # trilinear devoxelize: forward V -> F, backward F -> V
+    outs, inds, wgts = P.trilinear_devoxelize_forward(res, True, nc, grid)
+    gx = P.trilinear_devoxelize_backward_coords(gy, nc, res)
+    lhs, rhs = dot(outs, gy), dot(grid, gx)
+    assert abs(lhs - rhs) <= 1e-6 * norm(outs) * norm(gy), f"trilinear devoxelize adjoint identity: {lhs} vs {rhs}"
+    gx_generic = P.trilinear_devoxelize_backward(gy, inds, wgts, res)
+    assert abs(dot(grid, gx_generic) - lhs) <= 1e-6 * norm(outs) * norm(gy), "adjoint identity, backward from inds / wgts"
+    # the 8 weights of a point sum to 1: a constant grid interpolates to the same constant
+    ones = P.trilinear_devoxelize_forward(res, False, nc, torch.ones(b, 2, res ** 3, device="cuda"))[0]
+    assert float((ones - 1).abs().max()) <= 1e-6, "partition of unity"
+
+
 # ------------------------------------------------------------------------------------------------ pointnet ops
 PN_SHAPES = [
     dict(seed=41, b=2, c=5, n=1024, m=256, kind="rand"),
