@@ -11,6 +11,26 @@ namespace pcfm {
 // tiles shared by the CTA's warps; 32 candidates are tested per step, hits are compacted with ballot +
 // prefix-popcount so the output keeps the reference's "first U in index order" rule, with early exit.
 // =================================================================================================
+// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): each lane rounded exactly like the scalar instruction
+__device__ __forceinline__ unsigned long long nn_pack2(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long nn_sub2(unsigned long long a, unsigned long long b) {
+  unsigned long long r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ void nn_sq3x2(unsigned long long dx, unsigned long long dy, unsigned long long dz, float& lo,
+                                         float& hi) {  // sq3(): FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.)
+  unsigned long long t;
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(t));
+}
+
 constexpr int kBqWarps = 16;
 constexpr int kBqTile = 2048;
 
@@ -18,7 +38,7 @@ __global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* 
                                                                    const float* __restrict__ points, int n,
                                                                    int m, float r2, int u,
                                                                    int* __restrict__ out) {
-  __shared__ float px[kBqTile], py[kBqTile], pz[kBqTile];
+  __shared__ __align__(8) float px[kBqTile], py[kBqTile], pz[kBqTile];
   const int b = blockIdx.y;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int j = blockIdx.x * kBqWarps + wid;
@@ -42,16 +62,28 @@ __global__ void __launch_bounds__(kBqWarps * 32) ball_query_kernel(const float* 
     }
     __syncthreads();
     if (valid && cnt < u) {
-      for (int k0 = 0; k0 < len; k0 += 32) {
-        const int k = k0 + lane;
-        bool hit = false;
-        if (k < len) hit = sq3(cx - px[k], cy - py[k], cz - pz[k]) < r2;  // centre - point, strict <
-        const unsigned mask = __ballot_sync(0xffffffffu, hit);
-        if (mask) {
-          if (cnt == 0) first = base + k0 + __ffs(mask) - 1;
-          const int pos = cnt + __popc(mask & ((1u << lane) - 1u));
-          if (hit && pos < u) ob[pos] = base + k;
-          cnt += __popc(mask);
+      // 64 points per step: lane L tests the points 2L and 2L + 1 of the step with one packed evaluation (the three
+      // coordinate pairs arrive as LDS.64); hits are placed in index order: ranks from the two ballot masks
+      const unsigned long long cxp = nn_pack2(cx, cx), cyp = nn_pack2(cy, cy), czp = nn_pack2(cz, cz);
+      const unsigned lt = (1u << lane) - 1u;
+      for (int k0 = 0; k0 < len; k0 += 64) {
+        const int k = k0 + 2 * lane;                // kBqTile is a multiple of 64: the pair read stays inside the arrays
+        float d0, d1;
+        nn_sq3x2(nn_sub2(cxp, *reinterpret_cast<const unsigned long long*>(px + k)),
+                 nn_sub2(cyp, *reinterpret_cast<const unsigned long long*>(py + k)),
+                 nn_sub2(czp, *reinterpret_cast<const unsigned long long*>(pz + k)), d0, d1);  // centre - point
+        const bool h0 = k < len && d0 < r2, h1 = k + 1 < len && d1 < r2;                       // strict <
+        const unsigned m0 = __ballot_sync(0xffffffffu, h0), m1 = __ballot_sync(0xffffffffu, h1);
+        if (m0 | m1) {
+          if (cnt == 0) {
+            const int f0 = m0 ? 2 * (__ffs(m0) - 1) : 64, f1 = m1 ? 2 * (__ffs(m1) - 1) + 1 : 64;
+            first = base + k0 + min(f0, f1);
+          }
+          const int below = cnt + __popc(m0 & lt) + __popc(m1 & lt);  // hits at lower indices than 2L
+          if (h0 && below < u) ob[below] = base + k;
+          const int below1 = below + (h0 ? 1 : 0);
+          if (h1 && below1 < u) ob[below1] = base + k + 1;
+          cnt += __popc(m0) + __popc(m1);
           if (cnt >= u) break;
         }
       }
@@ -304,27 +336,6 @@ __global__ void __cluster_dims__(kFpsCl, 1, 1) __launch_bounds__(1024, 1)
 // through shared memory; strict-< insertion keeps the earliest centre on ties.
 // =================================================================================================
 constexpr int kNnTile = 2048;
-
-// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): each lane rounded exactly like the scalar instruction
-__device__ __forceinline__ unsigned long long nn_pack2(float lo, float hi) {
-  unsigned long long r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ unsigned long long nn_sub2(unsigned long long a, unsigned long long b) {
-  unsigned long long r;
-  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ void nn_sq3x2(unsigned long long dx, unsigned long long dy, unsigned long long dz, float& lo,
-                                         float& hi) {  // sq3(): FMUL(dy,dy); FFMA(dx,dx,.); FFMA(dz,dz,.)
-  unsigned long long t;
-  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(t) : "l"(dy));
-  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dx), "l"(t));
-  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(t) : "l"(dz), "l"(t));
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(t));
-}
-
 
 __global__ void __launch_bounds__(256) three_nn_kernel(const float* __restrict__ points,
                                                        const float* __restrict__ centers, int n, int m,
