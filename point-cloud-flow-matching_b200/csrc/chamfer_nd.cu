@@ -25,39 +25,87 @@ __device__ __forceinline__ float sqd(const float (&a)[D], const float* __restric
   return acc;
 }
 
+// packed fp32 pairs (sm_100 FADD2 / FMUL2 / FFMA2): each lane is rounded exactly like the scalar instruction
+typedef unsigned long long nd_f32x2;
+__device__ __forceinline__ nd_f32x2 nd_pack2(float lo, float hi) {
+  nd_f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ nd_f32x2 nd_sub2(nd_f32x2 a, nd_f32x2 b) {
+  nd_f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ nd_f32x2 nd_sq(nd_f32x2 d) {
+  nd_f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %1;" : "=l"(r) : "l"(d));
+  return r;
+}
+__device__ __forceinline__ nd_f32x2 nd_sqacc(nd_f32x2 d, nd_f32x2 acc) {
+  nd_f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %1, %2;" : "=l"(r) : "l"(d), "l"(acc));
+  return r;
+}
+
+// The other cloud sits in shared memory as D coordinate rows (SoA), so one LDS.128 per coordinate yields two register
+// PAIRS of columns and sqd() runs on packed fp32: two columns per instruction.  The running minimum is kept per group of
+// four columns (strict <: the first group that reaches the minimum wins) and resolved to its lowest column at the end by
+// recomputing the four (bit-identical) distances — the scheme of chamfer_nn_kernel (chamfer.cu).
 template <int D, int RA>
 __global__ void __launch_bounds__(kNdThreads)
     chamfer_nd_kernel(const float* __restrict__ own, const float* __restrict__ other, int n, int m,
                       float* __restrict__ dist, int* __restrict__ idx) {
-  __shared__ __align__(16) float tile[kNdTile * D];
+  __shared__ __align__(16) float tile[D][kNdTile + 4];  // + 4: the D rows of one column fall into different banks (transposing fill)
   const int b = blockIdx.y;
   const float* pa = own + (long long)b * n * D;
   const float* po = other + (long long)b * m * D;
   float a[RA][D], best[RA];
-  int bi[RA];
+  nd_f32x2 ap[RA][D];
+  int bk[RA];
   int row[RA];
 #pragma unroll
   for (int r = 0; r < RA; ++r) {
     row[r] = (blockIdx.x * RA + r) * kNdThreads + threadIdx.x;
     const int rr = min(row[r], n - 1);
 #pragma unroll
-    for (int k = 0; k < D; ++k) a[r][k] = pa[(long long)rr * D + k];
+    for (int k = 0; k < D; ++k) {
+      a[r][k] = pa[(long long)rr * D + k];
+      ap[r][k] = nd_pack2(a[r][k], a[r][k]);
+    }
     best[r] = __int_as_float(0x7f800000);  // +inf: the first candidate always wins, like `k==0 ||` in the reference
-    bi[r] = 0;
+    bk[r] = 0;
   }
   for (int t0 = 0; t0 < m; t0 += kNdTile) {
-    const int tn = min(kNdTile, m - t0);
+    const int tn = min(kNdTile, m - t0), tn4 = (tn + 3) & ~3;
     __syncthreads();
-    for (int i = threadIdx.x; i < tn * D; i += kNdThreads) tile[i] = po[(long long)t0 * D + i];
+    for (int i = threadIdx.x; i < tn4 * D; i += kNdThreads) {   // coalesced AoS read, transposed into the rows
+      const int jj = i / D, k = i - jj * D;
+      tile[k][jj] = jj < tn ? po[(long long)t0 * D + i] : __int_as_float(0x7f800000);  // padding: distance +inf
+    }
     __syncthreads();
-    for (int j = 0; j < tn; ++j) {
-      const float* o = tile + j * D;
+    for (int j = 0; j < tn4; j += 4) {
+      ulonglong2 q[D];
+#pragma unroll
+      for (int k = 0; k < D; ++k) q[k] = *reinterpret_cast<const ulonglong2*>(&tile[k][j]);  // (o_j, o_j+1) (o_j+2, o_j+3)
 #pragma unroll
       for (int r = 0; r < RA; ++r) {
-        const float d = sqd<D>(a[r], o);
-        if (d < best[r]) {  // strict: the lowest index keeps a tie (chamfer6D.cu:39-42 and the chunk merge :160-164)
-          best[r] = d;
-          bi[r] = t0 + j;
+        // the reference subtracts own from other, then y*y, fma(x,x,.), fma(z,z,.), ...  (sqd() above)
+        nd_f32x2 acc0 = nd_sq(nd_sub2(q[1].x, ap[r][1])), acc1 = nd_sq(nd_sub2(q[1].y, ap[r][1]));
+        acc0 = nd_sqacc(nd_sub2(q[0].x, ap[r][0]), acc0);
+        acc1 = nd_sqacc(nd_sub2(q[0].y, ap[r][0]), acc1);
+#pragma unroll
+        for (int k = 2; k < D; ++k) {
+          acc0 = nd_sqacc(nd_sub2(q[k].x, ap[r][k]), acc0);
+          acc1 = nd_sqacc(nd_sub2(q[k].y, ap[r][k]), acc1);
+        }
+        float d0, d1, d2, d3;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(acc0));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(d2), "=f"(d3) : "l"(acc1));
+        const float m4 = fminf(fminf(d0, d1), fminf(d2, d3));
+        if (m4 < best[r]) {  // strict: the lowest group keeps a tie (chamfer6D.cu:39-42 and the chunk merge :160-164)
+          best[r] = m4;
+          bk[r] = t0 + j;
         }
       }
     }
@@ -65,8 +113,17 @@ __global__ void __launch_bounds__(kNdThreads)
 #pragma unroll
   for (int r = 0; r < RA; ++r)
     if (row[r] < n) {
+      int bi = bk[r];
+      for (int t = 0; t < 4; ++t) {   // lowest column inside the winning group of four
+        const int k = bk[r] + t;
+        if (k >= m) break;
+        if (sqd<D>(a[r], po + (long long)k * D) == best[r]) {
+          bi = k;
+          break;
+        }
+      }
       dist[(long long)b * n + row[r]] = best[r];
-      idx[(long long)b * n + row[r]] = bi[r];
+      idx[(long long)b * n + row[r]] = bi;
     }
 }
 
