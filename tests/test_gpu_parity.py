@@ -490,6 +490,28 @@ def test_grouping_backward_forms(be, oracle, b, c, n, m, u, kind):
         assert_equal(got != 0, want != 0, f"sparsity pattern (grouping_bwd={opt})")
 
 
+@pytest.mark.parametrize("b,c,n,m", [(2, 5, 3000, 700), (1, 3, 4099, 60000), (1, 2, 50000, 240000), (1, 1, 7, 3)])
+def test_three_nn_backward_forms(be, oracle, b, c, n, m):
+    """3-NN interpolate backward as a scatter into a shared-memory row of the m centres (default; more than 55296
+    centres: slices with one CTA each; more than 229376: sorted segments) and as sorted-segment sums
+    (pcfm_set_option("three_nn_bwd", 1)), for arbitrary (idx, weight) triples, against the oracle."""
+    from pcfm import _lib
+    g = rng(700 + n + m)
+    idx = g.integers(0, m, size=(b, 3, n)).astype(np.int32)
+    w = g.random((b, 3, n)).astype(np.float32)
+    w /= w.sum(1, keepdims=True)
+    gy = g.standard_normal((b, c, n)).astype(np.float32)
+    want = oracle.three_nn_interpolate_backward(gy, idx, w, m)
+    for opt in (0, 1):
+        _lib.set_option("three_nn_bwd", opt)
+        try:
+            got = host(be.pvcnn.three_nearest_neighbors_interpolate_backward(cu(gy), cu(idx), cu(w), m))
+        finally:
+            _lib.set_option("three_nn_bwd", 0)
+        assert_close(got, want, f"3-NN interpolate backward (three_nn_bwd={opt})", atol_frac=1e-6)
+        assert_equal(got != 0, want != 0, f"sparsity pattern (three_nn_bwd={opt})")
+
+
 @pytest.mark.parametrize("kw", PN_SHAPES, ids=lambda k: f"{k['kind']}n{k['n']}m{k['m']}")
 def test_fps_ballquery_grouping_gather_3nn(be, oracle, ref, kw):
     pts, feat, cfeat = cases.pointnet_case(**kw)
