@@ -1,0 +1,3 @@
+mkdir -p gpurun_out
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 4 --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus 4 --steps 20 --warmup 3 > gpurun_out/r2_bench_n4.json 2> gpurun_out/r2_bench_n4.err
+tail -2 gpurun_out/r2_bench_n4.err | cut -c1-200; head -c 300 gpurun_out/r2_bench_n4.json
