@@ -111,6 +111,13 @@ def set_option(key, value):
         fn()
 
 
+# PCFM_B200_OPTIONS="pdl=0,plan=1": developer override, pcfm_set_option pairs applied at import (whole test-suite runs
+# under a non-default launch / plan-build mode: tests/gpu_scripts/option_matrix.sh)
+for _pair in filter(None, os.environ.get("PCFM_B200_OPTIONS", "").split(",")):
+    _k, _v = _pair.split("=")
+    set_option(_k.strip(), int(_v))
+
+
 def build_info():
     return lib.pcfm_build_info().decode()
 
